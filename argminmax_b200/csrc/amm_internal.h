@@ -1,0 +1,53 @@
+// amm_internal.h -- definitions shared by the translation units of libargminmax_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/argminmax_b200.h"
+
+namespace amm {
+extern thread_local int g_last_cuda_error;
+}
+
+#define AMM_CUDA(expr)                                  \
+  do {                                                  \
+    cudaError_t _e = (expr);                            \
+    if (_e != cudaSuccess) {                            \
+      amm::g_last_cuda_error = (int)_e;                 \
+      (void)cudaGetLastError();                         \
+      return AMM_ERR_CUDA;                              \
+    }                                                   \
+  } while (0)
+
+struct amm_host_pipeline;  // host_slice.cu
+
+// 14 policy slots (8 ints + 3 floats x 2 modes) x load-shape variants
+constexpr int AMM_POLICY_SLOTS = 14;
+constexpr int AMM_MAX_VARIANTS = 8;
+
+struct amm_workspace {
+  int device;
+  int sm_count;
+  int threads;      // CTA size
+  int ctas_per_sm;  // persistent CTAs per SM (capped by occupancy)
+  int variant;      // load shape, see kVariants in libamm.cu
+  int max_grid;
+  int occupancy[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // cached per current `threads`
+  void* partials;            // max_grid x 64 B
+  uint32_t* ticket;          // last-block-done counter (self-resetting)
+  amm_record* rec_dev;       // device record slot
+  amm_record* rec_host;      // pinned + mapped host record slot (host address)
+  amm_record* rec_host_dev;  // ... its device address
+  uint64_t seq;              // calls issued on this workspace
+  int last_grid, last_threads;
+  uint64_t launches;
+  amm_host_pipeline* pipe;  // lazily created by amm_host_argminmax
+};
+
+namespace amm {
+int set_device(int device);
+int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global_offset,
+           amm_workspace* ws, cudaStream_t stream, void* dev_record_out);
+void combine(const amm_record* recs, int count, int mode, uint64_t out[2]);
+void host_pipeline_destroy(amm_workspace* ws);
+}  // namespace amm

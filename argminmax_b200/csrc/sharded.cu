@@ -1,0 +1,204 @@
+// sharded.cu -- ShardedDeviceSlice<T>: one logical array split into consecutive
+// index ranges over the GPUs of one box, driven from ONE host thread.
+//
+// No reference sibling exists (the crate is single-threaded, single-device); the
+// algebra is the reference's own merge rule applied across devices: argmin/argmax
+// with first-occurrence tie-break is an associative reduction over (key, index)
+// (chunk merge src/simd/generic.rs:513-520, prefix/tail merge src/simd/task.rs:149-228).
+//
+// Per call: every device scans its shard with the ordinary kernel (global_offset =
+// shard start) on its own stream; the G 64-byte records are exchanged by ONE
+// ncclAllGather (G x 64 B over NVLink, latency-bound) enqueued on the same streams;
+// the gathered table is read back from device 0 and combined in ascending shard
+// order with strict compares.  NCCL is resolved with dlopen at run time so the
+// library has no link-time NCCL dependency and shares the copy already loaded by
+// the host process (e.g. torch's).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <string.h>
+
+#include <new>
+
+#include "amm_internal.h"
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef int ncclResult_t;  // 0 == ncclSuccess
+constexpr int kNcclUint8 = 1;
+
+struct NcclApi {
+  void* handle;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
+};
+
+bool load_nccl(NcclApi& api) {
+  memset(&api, 0, sizeof(api));
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return false;
+  api.CommInitAll = (decltype(api.CommInitAll))dlsym(api.handle, "ncclCommInitAll");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+  api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
+  api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+  return api.CommInitAll && api.CommDestroy && api.GroupStart && api.GroupEnd && api.AllGather;
+}
+
+constexpr int kMaxGpus = 16;
+
+}  // namespace
+
+struct amm_sharded {
+  int ngpu;
+  int devices[kMaxGpus];
+  amm_workspace* ws[kMaxGpus];
+  cudaStream_t streams[kMaxGpus];
+  amm_record* gathered[kMaxGpus];  // device, ngpu records each
+  amm_record* gathered_host;       // pinned, ngpu records
+  bool use_nccl;
+  NcclApi api;
+  ncclComm_t comms[kMaxGpus];
+};
+
+using namespace amm;
+
+extern "C" {
+
+int amm_sharded_destroy(amm_sharded* sh) {
+  if (!sh) return AMM_OK;
+  for (int g = 0; g < sh->ngpu; ++g) {
+    set_device(sh->devices[g]);
+    if (sh->streams[g]) {
+      cudaStreamSynchronize(sh->streams[g]);
+    }
+    if (sh->use_nccl && sh->comms[g]) sh->api.CommDestroy(sh->comms[g]);
+    if (sh->streams[g]) cudaStreamDestroy(sh->streams[g]);
+    if (sh->gathered[g]) cudaFree(sh->gathered[g]);
+    if (sh->ws[g]) amm_workspace_destroy(sh->ws[g]);
+  }
+  if (sh->gathered_host) cudaFreeHost(sh->gathered_host);
+  delete sh;
+  return AMM_OK;
+}
+
+int amm_sharded_create(int ngpu, const int* devices, amm_sharded** out) {
+  if (!out || ngpu < 1 || ngpu > kMaxGpus) return AMM_ERR_ARG;
+  *out = nullptr;
+  amm_sharded* sh = new (std::nothrow) amm_sharded();
+  if (!sh) return AMM_ERR_ARG;
+  memset(sh, 0, sizeof(*sh));
+  sh->ngpu = ngpu;
+  for (int g = 0; g < ngpu; ++g) sh->devices[g] = devices ? devices[g] : g;
+  for (int g = 0; g < ngpu; ++g) {
+    int rc = amm_workspace_create(sh->devices[g], &sh->ws[g]);
+    if (rc) {
+      amm_sharded_destroy(sh);
+      return rc;
+    }
+    cudaError_t e = cudaStreamCreateWithFlags(&sh->streams[g], cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+      e = cudaMalloc((void**)&sh->gathered[g], sizeof(amm_record) * (size_t)ngpu);
+    if (e != cudaSuccess) {
+      g_last_cuda_error = (int)e;
+      amm_sharded_destroy(sh);
+      return AMM_ERR_CUDA;
+    }
+  }
+  cudaError_t e = cudaHostAlloc((void**)&sh->gathered_host, sizeof(amm_record) * (size_t)ngpu,
+                                cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    amm_sharded_destroy(sh);
+    return AMM_ERR_CUDA;
+  }
+  sh->use_nccl = false;
+  if (ngpu > 1 && load_nccl(sh->api)) {
+    if (sh->api.CommInitAll(sh->comms, ngpu, sh->devices) == 0) {
+      sh->use_nccl = true;
+    } else {
+      memset(sh->comms, 0, sizeof(sh->comms));
+    }
+  }
+  *out = sh;
+  return AMM_OK;
+}
+
+int amm_sharded_uses_nccl(const amm_sharded* sh) { return (sh && sh->use_nccl) ? 1 : 0; }
+
+int amm_sharded_workspace(amm_sharded* sh, int g, amm_workspace** ws) {
+  if (!sh || !ws || g < 0 || g >= sh->ngpu) return AMM_ERR_ARG;
+  *ws = sh->ws[g];
+  return AMM_OK;
+}
+
+int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptrs,
+                          const uint64_t* shard_lens, int mode, uint64_t out[2]) {
+  if (!sh || !dev_ptrs || !shard_lens || !out) return AMM_ERR_ARG;
+  uint64_t total = 0;
+  for (int g = 0; g < sh->ngpu; ++g) total += shard_lens[g];
+  if (total == 0) return AMM_ERR_EMPTY;
+  // 1. every device scans its shard (async, one stream per device)
+  uint64_t offset = 0;
+  for (int g = 0; g < sh->ngpu; ++g) {
+    if (shard_lens[g] == 0) {  // an empty shard contributes a record without value / NaN
+      int rc = set_device(sh->devices[g]);
+      if (rc) return rc;
+      AMM_CUDA(cudaMemsetAsync(sh->ws[g]->rec_dev, 0, sizeof(amm_record), sh->streams[g]));
+    } else {
+      int rc = launch(dtype, dev_ptrs[g], shard_lens[g], mode, offset, sh->ws[g], sh->streams[g],
+                      nullptr);
+      if (rc) return rc;
+    }
+    offset += shard_lens[g];
+  }
+  const amm_record* table = nullptr;
+  amm_record local[kMaxGpus];
+  if (sh->use_nccl) {
+    // 2. one all-gather of the 64-byte records over NVLink, on the compute streams
+    if (sh->api.GroupStart() != 0) return AMM_ERR_NCCL;
+    for (int g = 0; g < sh->ngpu; ++g) {
+      if (sh->api.AllGather(sh->ws[g]->rec_dev, sh->gathered[g], sizeof(amm_record), kNcclUint8,
+                            sh->comms[g], sh->streams[g]) != 0) {
+        sh->api.GroupEnd();
+        return AMM_ERR_NCCL;
+      }
+    }
+    if (sh->api.GroupEnd() != 0) return AMM_ERR_NCCL;
+    int rc = set_device(sh->devices[0]);
+    if (rc) return rc;
+    AMM_CUDA(cudaMemcpyAsync(sh->gathered_host, sh->gathered[0],
+                             sizeof(amm_record) * (size_t)sh->ngpu, cudaMemcpyDeviceToHost,
+                             sh->streams[0]));
+    for (int g = 0; g < sh->ngpu; ++g) {
+      rc = set_device(sh->devices[g]);
+      if (rc) return rc;
+      AMM_CUDA(cudaStreamSynchronize(sh->streams[g]));
+    }
+    table = sh->gathered_host;
+  } else {
+    // no NCCL in this process: the records are read from each device's pinned slot
+    for (int g = 0; g < sh->ngpu; ++g) {
+      int rc = set_device(sh->devices[g]);
+      if (rc) return rc;
+      AMM_CUDA(cudaStreamSynchronize(sh->streams[g]));
+      if (shard_lens[g] == 0)
+        memset(&local[g], 0, sizeof(amm_record));
+      else
+        local[g] = *sh->ws[g]->rec_host;
+    }
+    table = local;
+  }
+  // 3. deterministic combine, ascending shard order
+  combine(table, sh->ngpu, mode, out);
+  return AMM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+/*
+ * argminmax_b200.h -- C ABI of the B200-native fused argmin+argmax library.
+ *
+ * This is the drop-in boundary for ONE hot path of the reference crate
+ * (jvdd/argminmax): `ArgMinMax::argminmax` / `NaNArgMinMax::nanargminmax` over a
+ * contiguous 1-D array of one of 11 primitive dtypes, for data that already
+ * lives in B200 HBM.  Each entry point below names the reference interface it
+ * stands in for (paths relative to the reference repository root).  The Rust
+ * side (`mod cuda`: DeviceSlice<T> / ShardedDeviceSlice<T>, see INTEGRATION.md
+ * and rust/) binds exactly these symbols through `extern "C"`.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no CUDA / torch types in any signature
+ *     (`stream` is a cudaStream_t passed as void*, NULL = legacy default stream).
+ *   - every function returns an amm_status (0 = ok).  The reference's signatures
+ *     are infallible and PANIC on empty input (src/scalar/generic.rs:182,
+ *     src/simd/task.rs:12); a binding turns any non-zero status into a panic.
+ *   - indices are uint64_t element indices (Rust usize on 64-bit hosts).
+ *   - the library only READS the caller's device memory; all scratch lives in the
+ *     amm_workspace handle; there is no hidden global state and NO CPU fallback:
+ *     without a usable CUDA device every compute entry point fails with
+ *     AMM_ERR_CUDA.
+ *   - one workspace must not be used by two calls at the same time; distinct
+ *     workspaces / streams are independent.
+ *
+ * Semantics (bit-exact with the reference's scalar implementation,
+ * src/scalar/generic.rs:181-217 and src/scalar/scalar_f16.rs:20-48,100-136):
+ *   mode AMM_IGNORE_NAN (ArgMinMax):  ints: plain order.  floats: NaNs are
+ *     skipped; all-NaN input -> (0,0); f32/f64 compare as IEEE values
+ *     (-0.0 == +0.0), f16 through the reference's i16 "ord" key (-0.0 < +0.0).
+ *   mode AMM_RETURN_NAN (NaNArgMinMax, floats only; ints ignore the mode): if
+ *     any NaN is present both outputs are the index of the FIRST NaN.
+ *   ties -> first occurrence, for min and for max, at every level.
+ */
+#ifndef ARGMINMAX_B200_H
+#define ARGMINMAX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMM_VERSION_MAJOR 0
+#define AMM_VERSION_MINOR 1
+
+/* dtype codes: the eleven dtypes of README.md:22 / src/lib.rs:657-664 */
+typedef enum amm_dtype {
+  AMM_I8 = 0, AMM_I16 = 1, AMM_I32 = 2, AMM_I64 = 3,
+  AMM_U8 = 4, AMM_U16 = 5, AMM_U32 = 6, AMM_U64 = 7,
+  AMM_F16 = 8, AMM_F32 = 9, AMM_F64 = 10,
+  AMM_DTYPE_COUNT = 11
+} amm_dtype;
+
+/* the dtype strategies of src/dtype_strategy.rs:6,15,24 collapsed to a run-time tag:
+   Int + FloatIgnoreNaN -> AMM_IGNORE_NAN, FloatReturnNaN -> AMM_RETURN_NAN */
+typedef enum amm_mode { AMM_IGNORE_NAN = 0, AMM_RETURN_NAN = 1 } amm_mode;
+
+typedef enum amm_status {
+  AMM_OK = 0,
+  AMM_ERR_EMPTY = 1,    /* n == 0: the reference asserts !arr.is_empty()            */
+  AMM_ERR_ARG = 2,      /* NULL pointer, unknown dtype / mode, bad handle           */
+  AMM_ERR_ALIGN = 3,    /* device pointer not aligned to sizeof(element)            */
+  AMM_ERR_CUDA = 4,     /* a CUDA call failed (amm_last_cuda_error() has the code)  */
+  AMM_ERR_NCCL = 5,     /* NCCL unavailable or a collective failed                  */
+  AMM_ERR_TOO_LARGE = 6 /* more than 2^32-2 scan tiles (>= 32 TiB of input)         */
+} amm_status;
+
+/*
+ * Per-device result record (64 bytes).  One record is what each GPU contributes
+ * to the cross-GPU combine (ShardedDeviceSlice): keys are the order-preserving
+ * signed-integer images of the element values (the reference's key transforms,
+ * src/simd/simd_u32.rs:56, src/simd/simd_f32_return_nan.rs:5-9,
+ * src/scalar/scalar_f16.rs:10-13) widened to 64 bit so that one combine routine
+ * serves every dtype.  Indices are GLOBAL (shard offset already added).
+ */
+typedef struct amm_record {
+  int64_t min_key;
+  uint64_t min_idx;
+  int64_t max_key;
+  uint64_t max_idx;
+  uint64_t nan_idx; /* index of the first NaN, UINT64_MAX if none seen           */
+  uint64_t flags;   /* AMM_REC_HAS_VALUE | AMM_REC_HAS_NAN                        */
+  uint64_t n;       /* elements scanned for this record                          */
+  uint64_t seq;     /* workspace call counter (written last)                     */
+} amm_record;
+#define AMM_REC_HAS_VALUE 1ull /* at least one non-NaN element (always set for ints) */
+#define AMM_REC_HAS_NAN 2ull
+#define AMM_NO_INDEX UINT64_MAX
+
+typedef struct amm_workspace amm_workspace; /* per-device scratch + pinned result slot */
+typedef struct amm_sharded amm_sharded;     /* one workspace + stream per GPU + NCCL comms */
+
+/* ------------------------------------------------------------------ lifecycle */
+/* Scratch for calls on CUDA device `device` (block partials, ticket counter,
+   64-B device record, 64-B pinned+mapped host record).  No reference analogue:
+   the CPU path needs no scratch. */
+int amm_workspace_create(int device, amm_workspace** ws);
+int amm_workspace_destroy(amm_workspace* ws);
+
+/* -------------------------------------------------- the path, single device */
+/*
+ * Fused argmin+argmax over `n` elements of `dtype` at DEVICE pointer `dev_ptr`.
+ * Replaces  <&[T] as ArgMinMax>::argminmax     src/lib.rs:272-412 (ints), :422-459 (floats)
+ *      and  <&[T] as NaNArgMinMax>::nanargminmax  src/lib.rs:541-576
+ * i.e. the whole SIMD backend below them (src/simd/generic.rs:670-786 ->
+ * src/simd/task.rs:4-55 -> src/simd/generic.rs:362-412, 487-543).
+ * Synchronous from the caller's view: launches on `stream`, waits, writes
+ * out[0] = argmin, out[1] = argmax.
+ */
+int amm_argminmax(int dtype, const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws,
+                  void* stream, uint64_t out[2]);
+
+/* dtype-suffixed symbols, one per `impl ArgMinMax for &[T]` instantiation
+   (src/lib.rs:657 ints, :660 f32/f64, :664 f16) */
+int amm_argminmax_i8(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_i16(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_i32(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_i64(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_u8(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_u16(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_u32(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_u64(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_f16(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_f32(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+int amm_argminmax_f64(const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws, void* stream, uint64_t out[2]);
+
+/*
+ * Single-output forms: ArgMinMax::argmin / argmax (src/lib.rs:170,185) and
+ * NaNArgMinMax::nanargmin / nanargmax (src/lib.rs:227,243).  The scan is
+ * bandwidth-bound, so these run the fused kernel and return one half -- which is
+ * literally how the reference defines them for the return-NaN strategy
+ * (src/simd/simd_f32_return_nan.rs:407-413).
+ */
+int amm_argmin(int dtype, const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws,
+               void* stream, uint64_t* out);
+int amm_argmax(int dtype, const void* dev_ptr, uint64_t n, int mode, amm_workspace* ws,
+               void* stream, uint64_t* out);
+
+/* ------------------------------------------ split-phase (async) single device */
+/*
+ * Enqueue the scan on `stream` and return immediately.  The 64-byte record lands
+ * in the workspace's device record (amm_workspace_device_record) and in its pinned
+ * host record; `global_offset` is added to every index (shard offset for
+ * ShardedDeviceSlice, 0 otherwise).  amm_workspace_wait() synchronises `stream`
+ * and turns the record into (argmin, argmax).  Used by the sharded driver, by
+ * torch.distributed ranks that all-gather records themselves, and by bench.py to
+ * time the kernel alone with events.
+ */
+int amm_argminmax_launch(int dtype, const void* dev_ptr, uint64_t n, int mode,
+                         uint64_t global_offset, amm_workspace* ws, void* stream,
+                         void* dev_record_out /* 64-B device buffer, NULL = workspace slot */);
+int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2]);
+int amm_workspace_device_record(amm_workspace* ws, void** dev_record /* amm_record* on device */);
+int amm_workspace_host_record(amm_workspace* ws, const amm_record** host_record);
+
+/*
+ * Deterministic first-index combine of `count` per-shard records given in
+ * ascending shard order (host memory).  Strict compares, so the lowest shard wins
+ * ties = global first occurrence -- the same rule as the reference's chunk merge
+ * (src/simd/generic.rs:513-520) and prefix/tail merge (src/simd/task.rs:149-228).
+ * Return-NaN: min over nan_idx wins.  No shard with a value (all NaN) -> (0,0).
+ */
+int amm_combine_records(const amm_record* records, int count, int mode, uint64_t out[2]);
+
+/* -------------------------------------------------- host slices (step before) */
+/*
+ * `&[T]` / Vec<T> in HOST memory (src/lib.rs:679-712): chunked, double-buffered
+ * H2D copies overlapped with the scan of the previous chunk; PCIe-bound.  `host_ptr`
+ * should be pinned for full speed (pageable works).  Staging buffers are allocated
+ * lazily inside the workspace.
+ */
+int amm_host_argminmax(int dtype, const void* host_ptr, uint64_t n, int mode, amm_workspace* ws,
+                       uint64_t out[2]);
+
+/* ---------------------------------------------- one array over several GPUs */
+/*
+ * ShardedDeviceSlice<T>: one process drives `ngpu` devices of one box.  Shard g
+ * is `shard_lens[g]` elements at `dev_ptrs[g]` on `devices[g]`; shards are
+ * consecutive index ranges of one logical array.  Each device scans its shard
+ * (same kernel), the 64-byte records are exchanged with ONE ncclAllGather over
+ * NVLink on the compute streams, then combined as in amm_combine_records.
+ */
+int amm_sharded_create(int ngpu, const int* devices, amm_sharded** sh);
+int amm_sharded_destroy(amm_sharded* sh);
+int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptrs,
+                          const uint64_t* shard_lens, int mode, uint64_t out[2]);
+/* 1 if the records travel through NCCL, 0 if NCCL could not be loaded and the
+   records are read from each device's pinned host record instead */
+int amm_sharded_uses_nccl(const amm_sharded* sh);
+/* the per-device workspace of shard g (e.g. to apply amm_workspace_set_tuning) */
+int amm_sharded_workspace(amm_sharded* sh, int g, amm_workspace** ws);
+
+/* ------------------------------------------------------------- diagnostics */
+const char* amm_status_string(int status);
+int amm_last_cuda_error(void);        /* cudaError_t of the last AMM_ERR_CUDA on this thread */
+size_t amm_dtype_size(int dtype);     /* bytes per element, 0 for an unknown dtype */
+int amm_version(void);                /* AMM_VERSION_MAJOR * 100 + AMM_VERSION_MINOR */
+
+/* Scan geometry knobs (benchmarks / tuning only; defaults are the tuned values).
+   threads: CTA size (multiple of 32, 64..1024); ctas_per_sm: persistent CTAs per SM;
+   variant: load shape, see amm_variant_name().  threads / ctas_per_sm <= 0 and
+   variant < 0 keep the current value. */
+int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, int variant);
+int amm_workspace_get_tuning(const amm_workspace* ws, int* threads, int* ctas_per_sm, int* variant,
+                             int* sm_count);
+int amm_variant_count(void);
+const char* amm_variant_name(int variant);
+/* grid size and kernels launched by the most recent amm_argminmax_launch on ws */
+int amm_workspace_last_launch(const amm_workspace* ws, int* grid, int* threads, uint64_t* launches_total);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARGMINMAX_B200_H */

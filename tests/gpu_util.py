@@ -1,0 +1,64 @@
+"""Helpers for the -m gpu tests: move numpy arrays into B200 HBM (torch is only the
+allocator here) and call the CUDA path through the C ABI."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import oracle
+from tests import golden_util as G
+
+NP_NAME = {np.dtype(v): k for k, v in G.NP.items()}
+
+
+def to_device(arr: np.ndarray, byte_offset: int = 0):
+    """-> (DeviceSlice over a device copy of `arr`, owner tensor).  `byte_offset` shifts the
+    start of the data inside a larger allocation (must be a multiple of the element size) so
+    that unaligned heads are exercised."""
+    import torch
+
+    from argminmax_b200 import DeviceSlice
+
+    arr = np.ascontiguousarray(arr)
+    name = NP_NAME[arr.dtype]
+    raw = torch.from_numpy(arr.view(np.uint8).copy())
+    buf = torch.empty(raw.numel() + byte_offset + 64, dtype=torch.uint8, device="cuda:0")
+    view = buf[byte_offset:byte_offset + raw.numel()]
+    view.copy_(raw)
+    torch.cuda.synchronize()
+    return DeviceSlice.from_torch(view, dtype=name), buf
+
+
+def random_array(dt: str, n: int, rng: np.random.Generator, f16_bits: bool = False) -> np.ndarray:
+    """The reference's bench/test distributions (dev_utils/src/utils.rs:29-84), seeded:
+    ints uniform over the full range; f32/f64 uniform BIT PATTERNS with NaN -> 0.0; f16 uniform
+    by value (or, with f16_bits, uniform bit patterns with NaN -> 0.0 to stress subnormals/-0)."""
+    T = G.NP[dt]
+    if dt == "f16" and not f16_bits:
+        return rng.uniform(-65504.0, 65504.0, n).astype(np.float16)
+    if dt == "f16":
+        a = rng.integers(0, 2**16, n, dtype=np.uint16).view(np.float16).copy()
+    elif dt == "f32":
+        a = rng.integers(0, 2**32, n, dtype=np.uint32).view(np.float32).copy()
+    elif dt == "f64":
+        a = rng.integers(0, 2**64, n, dtype=np.uint64).view(np.float64).copy()
+    else:
+        info = np.iinfo(T)
+        return rng.integers(info.min, info.max, n, dtype=T, endpoint=True)
+    a[np.isnan(a)] = 0
+    return a
+
+
+def modes_for(dt: str):
+    return (0, 1) if dt in G.FLOAT_DTYPES else (0,)
+
+
+def run_gpu(ds, mode: int):
+    return ds.nanargminmax() if mode == 1 else ds.argminmax()
+
+
+def assert_parity(arr: np.ndarray, mode: int, byte_offset: int = 0, what: str = ""):
+    ds, _keep = to_device(arr, byte_offset)
+    got = run_gpu(ds, mode)
+    exp = oracle.argminmax(arr, mode)
+    assert got == exp, f"{what} dtype={arr.dtype} n={arr.size} mode={mode} off={byte_offset}: gpu {got} != oracle {exp}"
+    return got
