@@ -7,7 +7,11 @@ from ._ffi import (AmmError, AmmRecord, EmptyInputError, DTYPES, DTYPE_SIZE, FLO
 from .device_slice import (DeviceSlice, HostSlice, ShardedDeviceSlice, Workspace,
                            combine_records, default_workspace)
 
+from .distributed import (DistributedShardedSlice, combine_across_ranks, exchange_records,
+                          shard_bounds)
+
 __all__ = [
+    "DistributedShardedSlice", "combine_across_ranks", "exchange_records", "shard_bounds",
     "AmmError", "AmmRecord", "EmptyInputError", "DTYPES", "DTYPE_SIZE", "FLOAT_DTYPES",
     "IGNORE_NAN", "RETURN_NAN", "lib", "lib_path", "DeviceSlice", "HostSlice",
     "ShardedDeviceSlice", "Workspace", "combine_records", "default_workspace",

@@ -64,6 +64,8 @@ SIGNATURES = {
     "amm_workspace_host_record": (_i, [_vp, ctypes.POINTER(ctypes.POINTER(AmmRecord))]),
     "amm_combine_records": (_i, [ctypes.POINTER(AmmRecord), _i, _i, _u64p]),
     "amm_host_argminmax": (_i, [_i, _vp, _u64, _i, _vp, _u64p]),
+    "amm_host_argminmax_record": (_i, [_i, _vp, _u64, _i, _u64, _vp, ctypes.POINTER(AmmRecord)]),
+    "amm_combine_records_launch": (_i, [_vp, _i, _i, _vp, _vp]),
     "amm_sharded_create": (_i, [_i, ctypes.POINTER(_i), ctypes.POINTER(_vp)]),
     "amm_sharded_destroy": (_i, [_vp]),
     "amm_sharded_argminmax": (_i, [_vp, _i, ctypes.POINTER(_vp), _u64p, _i, _u64p]),

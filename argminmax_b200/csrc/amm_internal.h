@@ -49,5 +49,6 @@ int set_device(int device);
 int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global_offset,
            amm_workspace* ws, cudaStream_t stream, void* dev_record_out);
 void combine(const amm_record* recs, int count, int mode, uint64_t out[2]);
+amm_record fold_records(const amm_record* recs, int count);
 void host_pipeline_destroy(amm_workspace* ws);
 }  // namespace amm

@@ -59,9 +59,9 @@ void host_pipeline_destroy(amm_workspace* ws) {
 
 using namespace amm;
 
-extern "C" int amm_host_argminmax(int dtype, const void* host_ptr, uint64_t n, int mode,
-                                  amm_workspace* ws, uint64_t out[2]) {
-  if (!ws || !host_ptr || !out) return AMM_ERR_ARG;
+static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint64_t global_offset,
+                     amm_workspace* ws, std::vector<amm_record>& recs) {
+  if (!ws || !host_ptr) return AMM_ERR_ARG;
   if (dtype < 0 || dtype >= AMM_DTYPE_COUNT) return AMM_ERR_ARG;
   if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
   if (n == 0) return AMM_ERR_EMPTY;
@@ -80,7 +80,7 @@ extern "C" int amm_host_argminmax(int dtype, const void* host_ptr, uint64_t n, i
   const uint64_t nchunks = (n + chunk_elems - 1) / chunk_elems;
   for (int i = 0; i < 2; ++i)
     amm_workspace_set_tuning(p->child[i], ws->threads, ws->ctas_per_sm, ws->variant);
-  std::vector<amm_record> recs;
+  recs.clear();
   recs.reserve((size_t)nchunks);
   const uint8_t* src = (const uint8_t*)host_ptr;
   for (uint64_t c = 0; c < nchunks; ++c) {
@@ -93,7 +93,8 @@ extern "C" int amm_host_argminmax(int dtype, const void* host_ptr, uint64_t n, i
     const uint64_t len = (n - begin) < chunk_elems ? (n - begin) : chunk_elems;
     AMM_CUDA(cudaMemcpyAsync(p->stage[s], src + begin * es, len * es, cudaMemcpyHostToDevice,
                              p->stream[s]));
-    rc = launch(dtype, p->stage[s], len, mode, begin, p->child[s], p->stream[s], nullptr);
+    rc = launch(dtype, p->stage[s], len, mode, global_offset + begin, p->child[s], p->stream[s],
+                nullptr);
     if (rc) return rc;
     ws->launches += 1;
   }
@@ -102,6 +103,28 @@ extern "C" int amm_host_argminmax(int dtype, const void* host_ptr, uint64_t n, i
     AMM_CUDA(cudaStreamSynchronize(p->stream[s]));
     recs.push_back(*p->child[s]->rec_host);
   }
+  return AMM_OK;
+}
+
+extern "C" int amm_host_argminmax(int dtype, const void* host_ptr, uint64_t n, int mode,
+                                  amm_workspace* ws, uint64_t out[2]) {
+  if (!out) return AMM_ERR_ARG;
+  std::vector<amm_record> recs;
+  int rc = host_scan(dtype, host_ptr, n, mode, 0, ws, recs);
+  if (rc) return rc;
   combine(recs.data(), (int)recs.size(), mode, out);
+  return AMM_OK;
+}
+
+// Same pipeline, but returns the shard-level 64-byte record (keys + global indices) so
+// that several host shards (ranks) can be combined with amm_combine_records.
+extern "C" int amm_host_argminmax_record(int dtype, const void* host_ptr, uint64_t n, int mode,
+                                         uint64_t global_offset, amm_workspace* ws,
+                                         amm_record* out) {
+  if (!out) return AMM_ERR_ARG;
+  std::vector<amm_record> recs;
+  int rc = host_scan(dtype, host_ptr, n, mode, global_offset, ws, recs);
+  if (rc) return rc;
+  *out = fold_records(recs.data(), (int)recs.size());
   return AMM_OK;
 }

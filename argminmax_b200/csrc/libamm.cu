@@ -143,40 +143,93 @@ int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global
   return dispatch(ws, dtype, mode, p, stream);
 }
 
-void combine(const amm_record* recs, int count, int mode, uint64_t out[2]) {
-  // ascending shard order + strict compares: the lowest shard wins ties, which is
-  // the global first occurrence (cf. src/simd/generic.rs:513-520).
+// Fold records (ascending shard order) into one record.  Strict compares on the key,
+// index as tie-break: the lowest shard wins ties, which is the global first
+// occurrence (cf. the reference's chunk merge, src/simd/generic.rs:513-520).
+amm_record fold_records(const amm_record* recs, int count) {
   bool have = false;
-  int64_t kmin = 0, kmax = 0;
-  uint64_t imin = 0, imax = 0, inan = AMM_NO_INDEX;
+  amm_record o;
+  memset(&o, 0, sizeof(o));
+  o.min_idx = o.max_idx = o.nan_idx = AMM_NO_INDEX;
   for (int g = 0; g < count; ++g) {
     const amm_record& r = recs[g];
-    if ((r.flags & AMM_REC_HAS_NAN) && r.nan_idx < inan) inan = r.nan_idx;
+    o.n += r.n;
+    if (r.seq > o.seq) o.seq = r.seq;
+    if ((r.flags & AMM_REC_HAS_NAN) && r.nan_idx < o.nan_idx) o.nan_idx = r.nan_idx;
     if (!(r.flags & AMM_REC_HAS_VALUE)) continue;
-    if (!have) {
-      kmin = r.min_key;
-      imin = r.min_idx;
-      kmax = r.max_key;
-      imax = r.max_idx;
-      have = true;
-    } else {
-      if (r.min_key < kmin || (r.min_key == kmin && r.min_idx < imin)) {
-        kmin = r.min_key;
-        imin = r.min_idx;
-      }
-      if (r.max_key > kmax || (r.max_key == kmax && r.max_idx < imax)) {
-        kmax = r.max_key;
-        imax = r.max_idx;
-      }
+    if (!have || r.min_key < o.min_key || (r.min_key == o.min_key && r.min_idx < o.min_idx)) {
+      o.min_key = r.min_key;
+      o.min_idx = r.min_idx;
     }
+    if (!have || r.max_key > o.max_key || (r.max_key == o.max_key && r.max_idx < o.max_idx)) {
+      o.max_key = r.max_key;
+      o.max_idx = r.max_idx;
+    }
+    have = true;
   }
-  if (mode == AMM_RETURN_NAN && inan != AMM_NO_INDEX) {
-    out[0] = out[1] = inan;  // first NaN for both (src/scalar/generic.rs:193-196)
-  } else if (!have) {
+  o.flags = (have ? AMM_REC_HAS_VALUE : 0ull) | (o.nan_idx != AMM_NO_INDEX ? AMM_REC_HAS_NAN : 0ull);
+  return o;
+}
+
+void combine(const amm_record* recs, int count, int mode, uint64_t out[2]) {
+  const amm_record o = fold_records(recs, count);
+  if (mode == AMM_RETURN_NAN && (o.flags & AMM_REC_HAS_NAN)) {
+    out[0] = out[1] = o.nan_idx;  // first NaN for both (src/scalar/generic.rs:193-196)
+  } else if (!(o.flags & AMM_REC_HAS_VALUE)) {
     out[0] = out[1] = 0;  // all NaN in ignore mode (src/simd/test_utils.rs:508-527)
   } else {
-    out[0] = imin;
-    out[1] = imax;
+    out[0] = o.min_idx;
+    out[1] = o.max_idx;
+  }
+}
+
+// Device-side twin of combine(): one thread folds `count` records (ascending shard
+// order, strict compares) into one record whose indices are the final answer, and
+// publishes it to the workspace's device + pinned host slots.  Lets a multi-GPU step
+// (scan -> all-gather -> combine) stay fully asynchronous on one stream.
+__global__ void combine_records_kernel(const amm_record* recs, int count, int mode,
+                                       amm_record* rec_dev, amm_record* rec_host, uint64_t seq) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  bool have = false;
+  int64_t kmin = 0, kmax = 0;
+  uint64_t imin = 0, imax = 0, inan = AMM_NO_INDEX, n = 0;
+  for (int g = 0; g < count; ++g) {
+    const amm_record r = recs[g];
+    n += r.n;
+    if ((r.flags & AMM_REC_HAS_NAN) && r.nan_idx < inan) inan = r.nan_idx;
+    if (!(r.flags & AMM_REC_HAS_VALUE)) continue;
+    if (!have || r.min_key < kmin || (r.min_key == kmin && r.min_idx < imin)) {
+      kmin = r.min_key;
+      imin = r.min_idx;
+    }
+    if (!have || r.max_key > kmax || (r.max_key == kmax && r.max_idx < imax)) {
+      kmax = r.max_key;
+      imax = r.max_idx;
+    }
+    have = true;
+  }
+  amm_record o;
+  o.min_key = kmin;
+  o.max_key = kmax;
+  o.min_idx = have ? imin : AMM_NO_INDEX;
+  o.max_idx = have ? imax : AMM_NO_INDEX;
+  o.nan_idx = inan;
+  o.flags = (have ? AMM_REC_HAS_VALUE : 0ull) | (inan != AMM_NO_INDEX ? AMM_REC_HAS_NAN : 0ull);
+  o.n = n;
+  o.seq = seq;
+  (void)mode;
+  *rec_dev = o;
+  if (rec_host != nullptr) {
+    volatile amm_record* h = rec_host;
+    h->min_key = o.min_key;
+    h->min_idx = o.min_idx;
+    h->max_key = o.max_key;
+    h->max_idx = o.max_idx;
+    h->nan_idx = o.nan_idx;
+    h->flags = o.flags;
+    h->n = o.n;
+    __threadfence_system();
+    h->seq = o.seq;
   }
 }
 
@@ -185,6 +238,19 @@ void combine(const amm_record* recs, int count, int mode, uint64_t out[2]) {
 using namespace amm;
 
 extern "C" {
+
+int amm_combine_records_launch(const void* dev_records, int count, int mode, amm_workspace* ws,
+                               void* stream) {
+  if (!dev_records || !ws || count < 1) return AMM_ERR_ARG;
+  if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
+  int rc = set_device(ws->device);
+  if (rc) return rc;
+  combine_records_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
+      (const amm_record*)dev_records, count, mode, ws->rec_dev, ws->rec_host_dev, ++ws->seq);
+  AMM_CUDA(cudaGetLastError());
+  ws->launches += 1;
+  return AMM_OK;
+}
 
 int amm_workspace_create(int device, amm_workspace** out) {
   if (out == nullptr) return AMM_ERR_ARG;

@@ -1,0 +1,130 @@
+"""One rank per GPU (torch.distributed): a logical array sharded into consecutive index
+ranges over the ranks of one job.
+
+Data path per call, on the rank's compute stream, nothing synchronous in between:
+    scan kernel (64-byte record, indices already global)
+ -> all_gather_into_tensor of the records   (NCCL over NVLink/NVSwitch: world x 64 B)
+ -> combine kernel (ascending rank order, strict compares => first occurrence)
+ -> (argmin, argmax) read from the workspace's pinned host slot.
+torch.distributed is plumbing only (rendezvous + the collective).  With the gloo backend
+(CPU tests) the record exchange and the host-side combine are exercised without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+from . import _ffi
+from ._ffi import DTYPES, FLOAT_DTYPES, IGNORE_NAN, RETURN_NAN, check, lib
+from .device_slice import DeviceSlice, combine_records
+
+
+def shard_bounds(n_total: int, world: int, rank: int, align_elems: int = 1) -> tuple[int, int]:
+    """Contiguous shard [begin, end) of rank `rank`: ceil(n/world) elements per rank, rounded up
+    to `align_elems` so every shard starts on a vector boundary."""
+    per = -(-n_total // world)
+    per = -(-per // align_elems) * align_elems
+    begin = min(n_total, per * rank)
+    end = min(n_total, begin + per)
+    return begin, end
+
+
+def exchange_records(local: _ffi.AmmRecord, group=None) -> list[_ffi.AmmRecord]:
+    """All-gather one 64-byte record per rank (host path; works with gloo and nccl)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    raw = bytes(local)
+    t = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+    if backend == "nccl":
+        t = t.cuda()
+    out = torch.empty(world * 64, dtype=torch.uint8, device=t.device)
+    dist.all_gather_into_tensor(out, t, group=group)
+    buf = out.cpu().numpy().tobytes()
+    return [_ffi.AmmRecord.from_buffer_copy(buf[i * 64:(i + 1) * 64]) for i in range(world)]
+
+
+def combine_across_ranks(local: _ffi.AmmRecord, mode: int, group=None) -> tuple[int, int]:
+    """Host-side: exchange records, then amm_combine_records in ascending rank order."""
+    return combine_records(exchange_records(local, group), mode)
+
+
+class DistributedShardedSlice:
+    """This rank's shard of a logical array; every rank must call the same methods in the same
+    order (they contain a collective).  Mirrors the ArgMinMax / NaNArgMinMax surface."""
+
+    def __init__(self, shard: DeviceSlice, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.shard = shard
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        dev = torch.device("cuda", shard.device)
+        lens = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        mine = torch.tensor([shard.n], dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(lens, mine, group=group)
+        lens = lens.cpu().tolist()
+        self.global_offset = int(sum(lens[: self.rank]))
+        self.n_total = int(sum(lens))
+        self._rec = torch.zeros(64, dtype=torch.uint8, device=dev)
+        self._gathered = torch.zeros(64 * self.world, dtype=torch.uint8, device=dev)
+
+    def __len__(self):
+        return self.n_total
+
+    def launch(self, mode: int = IGNORE_NAN) -> None:
+        """Enqueue scan -> all-gather -> combine on the current stream; no host sync."""
+        import torch
+        import torch.distributed as dist
+
+        stream = torch.cuda.current_stream().cuda_stream
+        s = self.shard
+        if s.n == 0:
+            self._rec.zero_()  # no value, no NaN
+        else:
+            rc = lib().amm_argminmax_launch(DTYPES[s.dtype], s.data_ptr, s.n, mode,
+                                            self.global_offset, s.workspace.handle, stream,
+                                            self._rec.data_ptr())
+            check(rc, "amm_argminmax_launch")
+        dist.all_gather_into_tensor(self._gathered, self._rec, group=self.group)
+        rc = lib().amm_combine_records_launch(self._gathered.data_ptr(), self.world, mode,
+                                              s.workspace.handle, stream)
+        check(rc, "amm_combine_records_launch")
+
+    def wait(self, mode: int = IGNORE_NAN) -> tuple[int, int]:
+        import torch
+        out = (ctypes.c_uint64 * 2)()
+        check(lib().amm_workspace_wait(self.shard.workspace.handle,
+                                       torch.cuda.current_stream().cuda_stream, mode, out),
+              "amm_workspace_wait")
+        return int(out[0]), int(out[1])
+
+    def _run(self, mode: int) -> tuple[int, int]:
+        if self.n_total == 0:
+            raise _ffi.EmptyInputError(_ffi.AMM_ERR_EMPTY, "DistributedShardedSlice")
+        self.launch(mode)
+        return self.wait(mode)
+
+    def argminmax(self):
+        return self._run(IGNORE_NAN)
+
+    def argmin(self):
+        return self._run(IGNORE_NAN)[0]
+
+    def argmax(self):
+        return self._run(IGNORE_NAN)[1]
+
+    def nanargminmax(self):
+        if self.shard.dtype not in FLOAT_DTYPES:
+            raise TypeError("NaNArgMinMax is only implemented for float dtypes")
+        return self._run(RETURN_NAN)
+
+    def nanargmin(self):
+        return self.nanargminmax()[0]
+
+    def nanargmax(self):
+        return self.nanargminmax()[1]

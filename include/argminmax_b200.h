@@ -163,6 +163,13 @@ int amm_workspace_host_record(amm_workspace* ws, const amm_record** host_record)
  * Return-NaN: min over nan_idx wins.  No shard with a value (all NaN) -> (0,0).
  */
 int amm_combine_records(const amm_record* records, int count, int mode, uint64_t out[2]);
+/* The same fold as a one-thread kernel on `stream`: reads `count` records from DEVICE memory
+   (e.g. the output of an NCCL all-gather) and publishes the folded record -- whose indices
+   are the final answer -- to the workspace's device + pinned host slots, so that a
+   multi-GPU step (scan -> all-gather -> combine) stays asynchronous.  amm_workspace_wait()
+   then yields (argmin, argmax). */
+int amm_combine_records_launch(const void* dev_records, int count, int mode, amm_workspace* ws,
+                               void* stream);
 
 /* -------------------------------------------------- host slices (step before) */
 /*
@@ -173,6 +180,10 @@ int amm_combine_records(const amm_record* records, int count, int mode, uint64_t
  */
 int amm_host_argminmax(int dtype, const void* host_ptr, uint64_t n, int mode, amm_workspace* ws,
                        uint64_t out[2]);
+/* Same, but yields the 64-byte record (indices offset by `global_offset`) so that host
+   shards held by several ranks can be combined with amm_combine_records. */
+int amm_host_argminmax_record(int dtype, const void* host_ptr, uint64_t n, int mode,
+                              uint64_t global_offset, amm_workspace* ws, amm_record* out);
 
 /* ---------------------------------------------- one array over several GPUs */
 /*

@@ -97,7 +97,7 @@ def test_duplicate_extrema_first_occurrence_across_tiles(dt):
         lo, hi = T(-60000.0), T(60000.0)
     else:
         info = np.iinfo(T)
-        a = rng.integers(info.min // 2, info.max // 2, n, dtype=T)
+        a = rng.integers(info.min // 2 + 1, info.max // 2, n, dtype=T)  # never hits lo / hi
         lo, hi = info.min, info.max
     pos_lo = [1_234_567, 1_234_568, 2_999_999, 4_999_999]
     pos_hi = [777_777, 2_000_000, 3_141_592, 4_999_998]
