@@ -305,9 +305,34 @@ int amm_argminmax_launch(int dtype, const void* dev_ptr, uint64_t n, int mode,
 
 int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2]) {
   if (!ws || !out) return AMM_ERR_ARG;
-  AMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  const amm_record r = *ws->rec_host;
-  if (r.seq != ws->seq) return AMM_ERR_CUDA;  // the kernel did not publish this call's record
+  // The kernel publishes the record into pinned host memory and writes `seq` last (after a
+  // system-scope fence), so the host can pick the answer up by polling that word -- a few
+  // microseconds sooner than cudaStreamSynchronize returns.  The stream is queried now and
+  // then so that a failed launch surfaces as an error instead of a hang; after the poll
+  // budget the call falls back to a blocking synchronize.
+  volatile amm_record* h = ws->rec_host;
+  const uint64_t want = ws->seq;
+  bool seen = false;
+  for (int spin = 0; spin < (1 << 22); ++spin) {
+    if (h->seq == want) {
+      seen = true;
+      break;
+    }
+    if ((spin & 0x3FFF) == 0x3FFF) {
+      cudaError_t q = cudaStreamQuery((cudaStream_t)stream);
+      if (q == cudaSuccess) break;  // finished: the record must be there now
+      if (q != cudaErrorNotReady) {
+        g_last_cuda_error = (int)q;
+        (void)cudaGetLastError();
+        return AMM_ERR_CUDA;
+      }
+    }
+  }
+  if (!seen) AMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  __sync_synchronize();
+  amm_record r;
+  memcpy(&r, (const void*)ws->rec_host, sizeof(r));
+  if (r.seq != want) return AMM_ERR_CUDA;  // the kernel did not publish this call's record
   combine(&r, 1, mode, out);
   return AMM_OK;
 }

@@ -298,6 +298,7 @@ def main() -> int:
     ms_per_step = ms_total / args.steps
     value = world * nbytes / ms_per_step / 1e6  # GB/s, aggregate
     clocks = sampler.summary(t_wall0, t_wall1)
+    main_launch = ws.last_launch()
 
     # ---- kernel-only duration of the dominant kernel (roofline), this rank, same stream
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -377,7 +378,7 @@ def main() -> int:
 
     sampler.stop_flag = True
     tuning = ws.get_tuning()
-    ll = ws.last_launch()
+    ll = main_launch
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "GB/s", "n_gpus": world,
