@@ -14,13 +14,15 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libargminmax_b200.so")
 STAMP = os.path.join(LIB_DIR, "build.stamp")
-SOURCES = ["libamm.cu", "host_slice.cu", "sharded.cu"]
-HEADERS = ["amm_internal.h", "policies.cuh", "scan_kernel.cuh",
+SOURCES = ["libamm.cu", "host_slice.cu", "sharded.cu", "scan_inst.cu"]
+HEADERS = ["amm_internal.h", "policies.cuh", "scan_kernel.cuh", "scan_launch.cuh",
            os.path.join("..", "..", "include", "argminmax_b200.h")]
+N_GROUPS = 7  # scan_inst.cu is compiled once per policy group (-DAMM_GROUP=k), in parallel
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+OBJ_DIR = os.path.join(HERE, "lib", "obj")
 
 
 def _nvcc() -> str:
@@ -46,22 +48,39 @@ def is_current() -> bool:
         return f.read().strip() == _fingerprint()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile the library if the sources changed since the last build. Returns its path."""
-    if not force and is_current():
-        return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+def _compile(nvcc: str, src: str, obj: str, extra: list[str], verbose: bool) -> str:
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
+        cmd[1:1] = ["-Xptxas", "-v"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+        raise RuntimeError(f"nvcc failed on {src} {extra}:\n" + proc.stdout + proc.stderr)
+    return proc.stderr
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the library if the sources changed since the last build. Returns its path.
+    Every translation unit is built with -gencode arch=compute_100a,code=sm_100a -lineinfo."""
+    if not force and is_current():
+        return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    jobs = [(src, os.path.join(OBJ_DIR, src.replace(".cu", ".o")), [])
+            for src in SOURCES if src != "scan_inst.cu"]
+    jobs += [("scan_inst.cu", os.path.join(OBJ_DIR, f"scan_inst_g{k}.o"), [f"-DAMM_GROUP={k}"])
+             for k in range(N_GROUPS)]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        logs = list(ex.map(lambda j: _compile(nvcc, j[0], j[1], j[2], verbose), jobs))
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH,
+            *[j[1] for j in jobs], "-ldl"]
+    proc = subprocess.run(link, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("link failed:\n" + proc.stdout + proc.stderr)
     with open(STAMP, "w") as f:
         f.write(_fingerprint())
     if verbose:
-        print(proc.stderr)
+        print("\n".join(logs))
     return LIB_PATH
 
 

@@ -71,11 +71,17 @@ SIGNATURES = {
     "amm_sharded_argminmax": (_i, [_vp, _i, ctypes.POINTER(_vp), _u64p, _i, _u64p]),
     "amm_sharded_uses_nccl": (_i, [_vp]),
     "amm_sharded_workspace": (_i, [_vp, _i, ctypes.POINTER(_vp)]),
+    "amm_device_count": (_i, [ctypes.POINTER(_i)]),
+    "amm_device_alloc": (_i, [_i, ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    "amm_device_free": (_i, [_i, _vp]),
+    "amm_copy_to_device": (_i, [_i, _vp, _vp, ctypes.c_size_t]),
+    "amm_copy_to_host": (_i, [_i, _vp, _vp, ctypes.c_size_t]),
     "amm_status_string": (ctypes.c_char_p, [_i]),
     "amm_last_cuda_error": (_i, []),
     "amm_dtype_size": (ctypes.c_size_t, [_i]),
     "amm_version": (_i, []),
     "amm_workspace_set_tuning": (_i, [_vp, _i, _i, _i]),
+    "amm_workspace_set_direct_threshold": (_i, [_vp, _u64]),
     "amm_workspace_get_tuning": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i),
                                       ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "amm_variant_count": (_i, []),

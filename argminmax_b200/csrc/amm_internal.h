@@ -23,7 +23,7 @@ struct amm_host_pipeline;  // host_slice.cu
 
 // 14 policy slots (8 ints + 3 floats x 2 modes) x load-shape variants
 constexpr int AMM_POLICY_SLOTS = 14;
-constexpr int AMM_MAX_VARIANTS = 8;
+constexpr int AMM_MAX_VARIANTS = 16;
 
 struct amm_workspace {
   int device;
@@ -32,13 +32,16 @@ struct amm_workspace {
   int ctas_per_sm;  // persistent CTAs per SM (capped by occupancy)
   int variant;      // load shape, see kVariants in libamm.cu
   int max_grid;
+  uint64_t direct_bytes;  // inputs up to this size take the one-pass latency kernel
+  int direct_threads, direct_ctas_per_sm;
   int occupancy[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // cached per current `threads`
   void* partials;            // max_grid x 64 B
   uint32_t* ticket;          // last-block-done counter (self-resetting)
   amm_record* rec_dev;       // device record slot
-  amm_record* rec_host;      // pinned + mapped host record slot (host address)
+  amm_record* rec_host;      // pinned + mapped host slot: record + checksum word (128 B)
   amm_record* rec_host_dev;  // ... its device address
   uint64_t seq;              // calls issued on this workspace
+  int publish_fence;
   int last_grid, last_threads;
   uint64_t launches;
   amm_host_pipeline* pipe;  // lazily created by amm_host_argminmax
@@ -48,6 +51,7 @@ namespace amm {
 int set_device(int device);
 int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global_offset,
            amm_workspace* ws, cudaStream_t stream, void* dev_record_out);
+bool read_host_slot(const amm_workspace* ws, uint64_t want, amm_record* out);
 void combine(const amm_record* recs, int count, int mode, uint64_t out[2]);
 amm_record fold_records(const amm_record* recs, int count);
 void host_pipeline_destroy(amm_workspace* ws);

@@ -78,8 +78,12 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
   const size_t es = amm_dtype_size(dtype);
   const uint64_t chunk_elems = p->chunk_bytes / es;
   const uint64_t nchunks = (n + chunk_elems - 1) / chunk_elems;
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 2; ++i) {
     amm_workspace_set_tuning(p->child[i], ws->threads, ws->ctas_per_sm, ws->variant);
+    p->child[i]->direct_bytes = ws->direct_bytes;
+    p->child[i]->direct_threads = ws->direct_threads;
+    p->child[i]->direct_ctas_per_sm = ws->direct_ctas_per_sm;
+  }
   recs.clear();
   recs.reserve((size_t)nchunks);
   const uint8_t* src = (const uint8_t*)host_ptr;
@@ -87,7 +91,9 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
     const int s = (int)(c & 1);
     if (c >= 2) {  // stage s is free once chunk c-2 has been scanned; harvest its record
       AMM_CUDA(cudaStreamSynchronize(p->stream[s]));
-      recs.push_back(*p->child[s]->rec_host);
+      amm_record r;
+      if (!read_host_slot(p->child[s], p->child[s]->seq, &r)) return AMM_ERR_CUDA;
+      recs.push_back(r);
     }
     const uint64_t begin = c * chunk_elems;
     const uint64_t len = (n - begin) < chunk_elems ? (n - begin) : chunk_elems;
@@ -101,7 +107,9 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
   for (uint64_t c = (nchunks >= 2 ? nchunks - 2 : 0); c < nchunks; ++c) {
     const int s = (int)(c & 1);
     AMM_CUDA(cudaStreamSynchronize(p->stream[s]));
-    recs.push_back(*p->child[s]->rec_host);
+    amm_record r;
+    if (!read_host_slot(p->child[s], p->child[s]->seq, &r)) return AMM_ERR_CUDA;
+    recs.push_back(r);
   }
   return AMM_OK;
 }

@@ -8,108 +8,74 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
 
 #include "../../include/argminmax_b200.h"
 #include "amm_internal.h"
-#include "scan_kernel.cuh"
+#include "scan_launch.cuh"
 
 namespace amm {
 
 thread_local int g_last_cuda_error = 0;
 
-// Load shapes compiled for every policy.  {VEC bytes, U vectors per thread per tile,
-// software prefetch}.  Tile = threads * U * VEC bytes.
-struct VariantDesc {
-  int vec, u, prefetch;
-  const char* name;
-};
-static const VariantDesc kVariants[] = {
-    {16, 4, 1, "v16x4_pf"},  // 0: 128-bit loads, 64 B/thread/tile, 2 tiles in flight
-    {32, 2, 1, "v32x2_pf"},  // 1: 256-bit loads, 64 B/thread/tile, 2 tiles in flight
-    {32, 4, 1, "v32x4_pf"},  // 2: 256-bit loads, 128 B/thread/tile, 2 tiles in flight
-    {16, 8, 0, "v16x8"},     // 3: 128-bit loads, 128 B/thread/tile, no prefetch
-    {32, 4, 0, "v32x4"},     // 4: 256-bit loads, 128 B/thread/tile, no prefetch
-    {16, 2, 1, "v16x2_pf"},  // 5: small tiles (latency-oriented)
-};
-constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+int launch_group0(int, amm_workspace*, ScanParams&, cudaStream_t);
+int launch_group1(int, amm_workspace*, ScanParams&, cudaStream_t);
+int launch_group2(int, amm_workspace*, ScanParams&, cudaStream_t);
+int launch_group3(int, amm_workspace*, ScanParams&, cudaStream_t);
+int launch_group4(int, amm_workspace*, ScanParams&, cudaStream_t);
+int launch_group5(int, amm_workspace*, ScanParams&, cudaStream_t);
+int launch_group6(int, amm_workspace*, ScanParams&, cudaStream_t);
 
-template <class P, int VEC, int U, bool PF>
-static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
-                      cudaStream_t stream) {
-  auto kernel = argminmax_scan_kernel<P, VEC, U, PF>;
-  int& occ = ws->occupancy[dtype_slot][variant];
-  if (occ == 0) {
-    int o = 0;
-    AMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, ws->threads, 0));
-    occ = o < 1 ? 1 : o;
-  }
-  const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
-  const uint64_t tile_vecs = (uint64_t)ws->threads * U;
-  // geometry: unaligned head | whole vectors | sub-vector tail
-  const uint64_t addr = (uint64_t)(uintptr_t)p.base;
-  uint64_t head = ((VEC - (addr % VEC)) % VEC) / sizeof(typename P::Elem);
-  if (head > p.n) head = p.n;
-  p.head_elems = head;
-  p.n_vec = (p.n - head) / vec_elems;
-  p.tail_start = head + p.n_vec * vec_elems;
-  const uint64_t full = p.n_vec / tile_vecs;
-  if (full >= 0xFFFFFFFEull) return AMM_ERR_TOO_LARGE;
-  p.n_full_tiles = (uint32_t)full;
-  p.rem_vecs = (uint32_t)(p.n_vec % tile_vecs);
-  const uint64_t tiles = full + (p.rem_vecs ? 1 : 0);
-  int per_sm = ws->ctas_per_sm < occ ? ws->ctas_per_sm : occ;
-  uint64_t grid = (uint64_t)ws->sm_count * (uint64_t)per_sm;
-  if (grid > tiles) grid = tiles;
-  if (grid < 1) grid = 1;
-  if (grid > (uint64_t)ws->max_grid) grid = (uint64_t)ws->max_grid;
-  kernel<<<(unsigned)grid, ws->threads, 0, stream>>>(p);
-  AMM_CUDA(cudaGetLastError());
-  ws->last_grid = (int)grid;
-  ws->last_threads = ws->threads;
-  ws->launches += 1;
-  return AMM_OK;
-}
-
-template <class P>
-static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStream_t stream) {
-  switch (ws->variant) {
-    case 0: return launch_one<P, 16, 4, true>(ws, p, dtype_slot, 0, stream);
-    case 1: return launch_one<P, 32, 2, true>(ws, p, dtype_slot, 1, stream);
-    case 2: return launch_one<P, 32, 4, true>(ws, p, dtype_slot, 2, stream);
-    case 3: return launch_one<P, 16, 8, false>(ws, p, dtype_slot, 3, stream);
-    case 4: return launch_one<P, 32, 4, false>(ws, p, dtype_slot, 4, stream);
-    case 5: return launch_one<P, 16, 2, true>(ws, p, dtype_slot, 5, stream);
-    default: return AMM_ERR_ARG;
+static int launch_slot(int slot, amm_workspace* ws, ScanParams& p, cudaStream_t s) {
+  switch (slot) {
+    case 0: case 4: return launch_group0(slot, ws, p, s);
+    case 1: case 5: return launch_group1(slot, ws, p, s);
+    case 2: case 6: return launch_group2(slot, ws, p, s);
+    case 3: case 7: return launch_group3(slot, ws, p, s);
+    case 8: case 9: return launch_group4(slot, ws, p, s);
+    case 10: case 11: return launch_group5(slot, ws, p, s);
+    default: return launch_group6(slot, ws, p, s);
   }
 }
 
-// The B200 counterpart of the reference's strategy dispatch
-// (Int / FloatIgnoreNaN / FloatReturnNaN, src/dtype_strategy.rs + src/lib.rs:272-664).
+// The kernels are instantiated in scan_inst.cu, compiled once per policy group (parallel
+// build); this is the strategy dispatch (Int / FloatIgnoreNaN / FloatReturnNaN,
+// src/dtype_strategy.rs + src/lib.rs:272-664) down to a policy slot.
 static int dispatch(amm_workspace* ws, int dtype, int mode, ScanParams& p, cudaStream_t stream) {
   const bool ret = (mode == AMM_RETURN_NAN);
+  int slot;
   switch (dtype) {
-    case AMM_I8: return launch_variant<PolInt8<true>>(ws, p, 0, stream);
-    case AMM_I16: return launch_variant<PolInt16<true>>(ws, p, 1, stream);
-    case AMM_I32: return launch_variant<PolInt32<true>>(ws, p, 2, stream);
-    case AMM_I64: return launch_variant<PolInt64<true>>(ws, p, 3, stream);
-    case AMM_U8: return launch_variant<PolInt8<false>>(ws, p, 4, stream);
-    case AMM_U16: return launch_variant<PolInt16<false>>(ws, p, 5, stream);
-    case AMM_U32: return launch_variant<PolInt32<false>>(ws, p, 6, stream);
-    case AMM_U64: return launch_variant<PolInt64<false>>(ws, p, 7, stream);
-    case AMM_F16:
-      return ret ? launch_variant<PolF16<MODE_RETURN>>(ws, p, 9, stream)
-                 : launch_variant<PolF16<MODE_IGNORE>>(ws, p, 8, stream);
-    case AMM_F32:
-      return ret ? launch_variant<PolF32<MODE_RETURN>>(ws, p, 11, stream)
-                 : launch_variant<PolF32<MODE_IGNORE>>(ws, p, 10, stream);
-    case AMM_F64:
-      return ret ? launch_variant<PolF64<MODE_RETURN>>(ws, p, 13, stream)
-                 : launch_variant<PolF64<MODE_IGNORE>>(ws, p, 12, stream);
+    case AMM_I8: slot = 0; break;
+    case AMM_I16: slot = 1; break;
+    case AMM_I32: slot = 2; break;
+    case AMM_I64: slot = 3; break;
+    case AMM_U8: slot = 4; break;
+    case AMM_U16: slot = 5; break;
+    case AMM_U32: slot = 6; break;
+    case AMM_U64: slot = 7; break;
+    case AMM_F16: slot = ret ? 9 : 8; break;
+    case AMM_F32: slot = ret ? 11 : 10; break;
+    case AMM_F64: slot = ret ? 13 : 12; break;
     default: return AMM_ERR_ARG;
   }
+  return launch_slot(slot, ws, p, stream);
+}
+
+// Pinned host slot = 8 record words + 1 checksum word (see publish_record).  True when the
+// slot holds the complete record of call `want`.
+bool read_host_slot(const amm_workspace* ws, uint64_t want, amm_record* out) {
+  const volatile uint64_t* h = reinterpret_cast<const volatile uint64_t*>(ws->rec_host);
+  if (h[7] != want) return false;
+  uint64_t w[9];
+  for (int i = 0; i < 9; ++i) w[i] = h[i];
+  uint64_t c = 0xA5A5C3C3F00DBEEFull;
+  for (int i = 0; i < 8; ++i) c ^= w[i];
+  if (c != w[8] || w[7] != want) return false;
+  memcpy(out, w, sizeof(amm_record));
+  return true;
 }
 
 int set_device(int device) {
@@ -140,6 +106,7 @@ int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global
   p.rec_host = ws->rec_host_dev;
   p.seq = ++ws->seq;
   p.mode = mode;
+  p.publish_fence = ws->publish_fence;
   return dispatch(ws, dtype, mode, p, stream);
 }
 
@@ -218,19 +185,11 @@ __global__ void combine_records_kernel(const amm_record* recs, int count, int mo
   o.n = n;
   o.seq = seq;
   (void)mode;
-  *rec_dev = o;
-  if (rec_host != nullptr) {
-    volatile amm_record* h = rec_host;
-    h->min_key = o.min_key;
-    h->min_idx = o.min_idx;
-    h->max_key = o.max_key;
-    h->max_idx = o.max_idx;
-    h->nan_idx = o.nan_idx;
-    h->flags = o.flags;
-    h->n = o.n;
-    __threadfence_system();
-    h->seq = o.seq;
-  }
+  ScanParams p;
+  p.rec_dev = rec_dev;
+  p.rec_host = rec_host;
+  p.publish_fence = 0;
+  publish_record(p, o);
 }
 
 }  // namespace amm
@@ -270,6 +229,12 @@ int amm_workspace_create(int device, amm_workspace** out) {
   ws->threads = 512;
   ws->ctas_per_sm = 2;
   ws->variant = 0;
+  ws->direct_bytes = (uint64_t)1 << 20;
+  ws->direct_threads = 256;
+  ws->direct_ctas_per_sm = 2;
+  if (getenv("AMM_DIRECT_BYTES")) ws->direct_bytes = strtoull(getenv("AMM_DIRECT_BYTES"), nullptr, 10);
+  if (getenv("AMM_DIRECT_THREADS")) ws->direct_threads = atoi(getenv("AMM_DIRECT_THREADS"));
+  if (getenv("AMM_DIRECT_CTAS")) ws->direct_ctas_per_sm = atoi(getenv("AMM_DIRECT_CTAS"));
   ws->max_grid = ws->sm_count * 32;
   // partials sized for the widest Best<int64_t> (40 B) -> 64 B slots
   AMM_CUDA(cudaMalloc(&ws->partials, (size_t)ws->max_grid * 64));
@@ -277,8 +242,9 @@ int amm_workspace_create(int device, amm_workspace** out) {
   AMM_CUDA(cudaMemset(ws->ticket, 0, 256));
   AMM_CUDA(cudaMalloc((void**)&ws->rec_dev, sizeof(amm_record)));
   AMM_CUDA(cudaMemset(ws->rec_dev, 0, sizeof(amm_record)));
-  AMM_CUDA(cudaHostAlloc((void**)&ws->rec_host, sizeof(amm_record), cudaHostAllocMapped));
-  memset(ws->rec_host, 0, sizeof(amm_record));
+  AMM_CUDA(cudaHostAlloc((void**)&ws->rec_host, 128, cudaHostAllocMapped));
+  memset(ws->rec_host, 0, 128);
+  ws->publish_fence = getenv("AMM_PUBLISH_FENCE") ? atoi(getenv("AMM_PUBLISH_FENCE")) : 0;
   AMM_CUDA(cudaHostGetDevicePointer((void**)&ws->rec_host_dev, ws->rec_host, 0));
   AMM_CUDA(cudaDeviceSynchronize());
   *out = ws;
@@ -310,15 +276,12 @@ int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2
   // microseconds sooner than cudaStreamSynchronize returns.  The stream is queried now and
   // then so that a failed launch surfaces as an error instead of a hang; after the poll
   // budget the call falls back to a blocking synchronize.
-  volatile amm_record* h = ws->rec_host;
   const uint64_t want = ws->seq;
+  amm_record r;
   bool seen = false;
-  for (int spin = 0; spin < (1 << 22); ++spin) {
-    if (h->seq == want) {
-      seen = true;
-      break;
-    }
-    if ((spin & 0x3FFF) == 0x3FFF) {
+  for (int spin = 0; spin < (1 << 22) && !seen; ++spin) {
+    seen = read_host_slot(ws, want, &r);
+    if (!seen && (spin & 0x3FFF) == 0x3FFF) {
       cudaError_t q = cudaStreamQuery((cudaStream_t)stream);
       if (q == cudaSuccess) break;  // finished: the record must be there now
       if (q != cudaErrorNotReady) {
@@ -328,11 +291,10 @@ int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2
       }
     }
   }
-  if (!seen) AMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  __sync_synchronize();
-  amm_record r;
-  memcpy(&r, (const void*)ws->rec_host, sizeof(r));
-  if (r.seq != want) return AMM_ERR_CUDA;  // the kernel did not publish this call's record
+  if (!seen) {
+    AMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (!read_host_slot(ws, want, &r)) return AMM_ERR_CUDA;  // record never published
+  }
   combine(&r, 1, mode, out);
   return AMM_OK;
 }
@@ -402,6 +364,42 @@ int amm_combine_records(const amm_record* records, int count, int mode, uint64_t
   return AMM_OK;
 }
 
+/* ---- device memory helpers (what DeviceSlice::from_slice needs on the Rust side) ---- */
+int amm_device_count(int* count) {
+  if (!count) return AMM_ERR_ARG;
+  AMM_CUDA(cudaGetDeviceCount(count));
+  return AMM_OK;
+}
+
+int amm_device_alloc(int device, size_t bytes, void** dev_ptr) {
+  if (!dev_ptr) return AMM_ERR_ARG;
+  int rc = set_device(device);
+  if (rc) return rc;
+  AMM_CUDA(cudaMalloc(dev_ptr, bytes ? bytes : 1));
+  return AMM_OK;
+}
+
+int amm_device_free(int device, void* dev_ptr) {
+  int rc = set_device(device);
+  if (rc) return rc;
+  AMM_CUDA(cudaFree(dev_ptr));
+  return AMM_OK;
+}
+
+int amm_copy_to_device(int device, void* dst_dev, const void* src_host, size_t bytes) {
+  int rc = set_device(device);
+  if (rc) return rc;
+  AMM_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+  return AMM_OK;
+}
+
+int amm_copy_to_host(int device, void* dst_host, const void* src_dev, size_t bytes) {
+  int rc = set_device(device);
+  if (rc) return rc;
+  AMM_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+  return AMM_OK;
+}
+
 const char* amm_status_string(int status) {
   switch (status) {
     case AMM_OK: return "ok";
@@ -444,6 +442,12 @@ int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, in
     if (variant >= kNumVariants) return AMM_ERR_ARG;
     ws->variant = variant;
   }
+  return AMM_OK;
+}
+
+int amm_workspace_set_direct_threshold(amm_workspace* ws, uint64_t bytes) {
+  if (!ws) return AMM_ERR_ARG;
+  ws->direct_bytes = bytes;
   return AMM_OK;
 }
 

@@ -57,6 +57,7 @@ struct ScanParams {
   amm_record* rec_host;    // pinned + mapped host record slot (device address) or nullptr
   uint64_t seq;
   int mode;
+  int publish_fence;  // debug: also issue a system-scope fence after publishing
 };
 
 // (key, position) candidates for min, max and first NaN.  Positions are tile ids in
@@ -130,27 +131,36 @@ __device__ __forceinline__ Best<Key> block_reduce(Best<Key> b, Best<Key>* smem /
 }
 
 // ------------------------------------------------------------- streaming loads
-template <int VEC>
+// Read-once data: non-coherent path, no L1 allocation.  HINT selects the L2 prefetch-size
+// qualifier (0: none, 1: .L2::128B, 2: .L2::256B).
+template <int VEC, int HINT = 2>
 struct VecLoad;
-template <>
-struct VecLoad<16> {
+#define AMM_LD_V4(QUAL)                                                              \
+  asm volatile("ld.global.nc.L1::no_allocate" QUAL ".v4.u32 {%0,%1,%2,%3}, [%4];"    \
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])                      \
+               : "l"(p))
+#define AMM_LD_V8(QUAL)                                                                      \
+  asm volatile("ld.global.nc.L1::no_allocate" QUAL ".v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" \
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]),     \
+                 "=r"(w[6]), "=r"(w[7])                                                      \
+               : "l"(p))
+template <int HINT>
+struct VecLoad<16, HINT> {
   static constexpr int NW = 4;
   static __device__ __forceinline__ void ld(const uint8_t* p, uint32_t (&w)[4]) {
-    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
-                 : "l"(p));
+    if (HINT == 0) AMM_LD_V4("");
+    if (HINT == 1) AMM_LD_V4(".L2::128B");
+    if (HINT == 2) AMM_LD_V4(".L2::256B");
   }
 };
-template <>
-struct VecLoad<32> {
+template <int HINT>
+struct VecLoad<32, HINT> {
   static constexpr int NW = 8;
   // 256-bit load: new on sm_100 (SASS LDG.E.NA.ENL2.LTC256B.256.CONSTANT)
   static __device__ __forceinline__ void ld(const uint8_t* p, uint32_t (&w)[8]) {
-    asm volatile(
-        "ld.global.nc.L1::no_allocate.L2::256B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]),
-          "=r"(w[7])
-        : "l"(p));
+    if (HINT == 0) AMM_LD_V8("");
+    if (HINT == 1) AMM_LD_V8(".L2::128B");
+    if (HINT == 2) AMM_LD_V8(".L2::256B");
   }
 };
 
@@ -190,29 +200,240 @@ __device__ __forceinline__ void fold_tile(const uint32_t (&v)[U][NW], uint32_t t
   r.tnan = (has_nan && r.tnan == TILE_NONE) ? tile_id : r.tnan;
 }
 
-// Exact lexicographic (key, index) scan of elements [begin, end).
-template <class P>
+// Exact (key, index) scan of elements [begin, end) by the whole CTA, 4 independent loads
+// in flight per thread.  ASCENDING: the caller guarantees this thread has not yet seen any
+// index >= begin, so a strict compare keeps the first occurrence; otherwise ranges may come
+// in any order and the full lexicographic rule is applied.
+template <class P, bool ASCENDING>
 __device__ __forceinline__ void exact_range(const uint8_t* base, uint64_t begin, uint64_t end,
                                             Best<typename P::Key>& b) {
   using Elem = typename P::Elem;
   using Key = typename P::Key;
   const Elem* e = reinterpret_cast<const Elem*>(base);
-  for (uint64_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
-    Key k;
-    bool valid, is_nan;
-    P::classify(e[i], k, valid, is_nan);
-    if (valid) {
-      b.merge_min(k, i);
-      b.merge_max(k, i);
+  constexpr int UN = 4;
+  for (uint64_t i0 = begin + threadIdx.x; i0 < end; i0 += (uint64_t)UN * blockDim.x) {
+    Elem raw[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const uint64_t i = i0 + (uint64_t)u * blockDim.x;
+      raw[u] = (i < end) ? e[i] : Elem(0);
     }
-    if (P::TRACK_NAN && is_nan && i < b.pnan) b.pnan = i;
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const uint64_t i = i0 + (uint64_t)u * blockDim.x;
+      if (i < end) {
+        Key k;
+        bool valid, is_nan;
+        P::classify(raw[u], k, valid, is_nan);
+        if (valid) {
+          if (ASCENDING) {
+            if (k < b.kmin || b.pmin == POS_NONE) {
+              b.kmin = k;
+              b.pmin = i;
+            }
+            if (k > b.kmax || b.pmax == POS_NONE) {
+              b.kmax = k;
+              b.pmax = i;
+            }
+          } else {
+            b.merge_min(k, i);
+            b.merge_max(k, i);
+          }
+        }
+        if (P::TRACK_NAN && is_nan && i < b.pnan) b.pnan = i;
+      }
+    }
   }
 }
 
-template <class P, int VEC, int U, bool PREFETCH>
-__global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanParams p) {
+// Element e of a vector held as 32-bit words (static indices only: stays in registers).
+template <class P, int NW>
+__device__ __forceinline__ typename P::Elem vec_elem(const uint32_t (&w)[NW], int e) {
+  using Elem = typename P::Elem;
+  if (sizeof(Elem) == 1) return (Elem)((w[e >> 2] >> (8 * (e & 3))) & 0xFFu);
+  if (sizeof(Elem) == 2) return (Elem)((w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
+  if (sizeof(Elem) == 4) return (Elem)w[e];
+  return (Elem)(((uint64_t)w[2 * e + 1] << 32) | (uint64_t)w[2 * e]);
+}
+
+// Exact lexicographic (key, index) scan of ONE streaming tile (0-based id `tile0`) with the
+// same vector loads and thread->vector mapping as the streaming phase: one round trip to
+// memory for the whole tile.
+template <class P, int VEC, int U>
+__device__ __forceinline__ void exact_tile(const uint8_t* main_base, uint64_t head_elems,
+                                           uint64_t tile0, uint64_t n_vec,
+                                           Best<typename P::Key>& b) {
   using Key = typename P::Key;
   constexpr int NW = VecLoad<VEC>::NW;
+  constexpr int VE = VEC / sizeof(typename P::Elem);
+  const uint64_t v0 = tile0 * ((uint64_t)blockDim.x * U) + threadIdx.x;
+  uint32_t w[U][NW];
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const uint64_t vi = v0 + (uint64_t)j * blockDim.x;
+    if (vi < n_vec) VecLoad<VEC>::ld(main_base + vi * VEC, w[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < U; ++j) {
+    const uint64_t vi = v0 + (uint64_t)j * blockDim.x;
+    if (vi < n_vec) {
+      const uint64_t i0 = head_elems + vi * VE;
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        Key k;
+        bool valid, is_nan;
+        P::classify(vec_elem<P, NW>(w[j], e), k, valid, is_nan);
+        if (valid) {
+          b.merge_min(k, i0 + e);
+          b.merge_max(k, i0 + e);
+        }
+        if (P::TRACK_NAN && is_nan && i0 + e < b.pnan) b.pnan = i0 + e;
+      }
+    }
+  }
+}
+
+// Publish one record to the device slot and (if mapped) the pinned host slot.
+// The host polls the pinned slot.  Instead of ordering the eight words with a system-scope
+// fence (which costs microseconds on the PCIe path), a ninth word carries a checksum over
+// the other eight: the host accepts the slot only when `seq` matches the call AND the
+// checksum matches, so a torn / partially arrived record is simply polled again.
+__device__ __forceinline__ uint64_t record_checksum(const amm_record& r) {
+  return r.min_key ^ r.min_idx ^ r.max_key ^ r.max_idx ^ r.nan_idx ^ r.flags ^ r.n ^ r.seq ^
+         0xA5A5C3C3F00DBEEFull;
+}
+
+__device__ __forceinline__ void publish_record(const ScanParams& p, const amm_record& r) {
+  *p.rec_dev = r;
+  if (p.rec_host != nullptr) {
+    volatile uint64_t* h = reinterpret_cast<volatile uint64_t*>(p.rec_host);
+    h[0] = (uint64_t)r.min_key;
+    h[1] = r.min_idx;
+    h[2] = (uint64_t)r.max_key;
+    h[3] = r.max_idx;
+    h[4] = r.nan_idx;
+    h[5] = r.flags;
+    h[6] = r.n;
+    h[7] = r.seq;
+    h[8] = record_checksum(r);
+    if (p.publish_fence) __threadfence_system();
+  }
+}
+
+template <typename Key>
+__device__ __forceinline__ amm_record make_record(const ScanParams& p, const Best<Key>& x) {
+  amm_record r;
+  const bool has_value = x.pmin != POS_NONE;
+  const bool has_nan = x.pnan != POS_NONE;
+  r.min_key = has_value ? (int64_t)x.kmin : 0;
+  r.max_key = has_value ? (int64_t)x.kmax : 0;
+  r.min_idx = has_value ? x.pmin + p.global_offset : AMM_NO_INDEX;
+  r.max_idx = has_value ? x.pmax + p.global_offset : AMM_NO_INDEX;
+  r.nan_idx = has_nan ? x.pnan + p.global_offset : AMM_NO_INDEX;
+  r.flags = (has_value ? AMM_REC_HAS_VALUE : 0ull) | (has_nan ? AMM_REC_HAS_NAN : 0ull);
+  r.n = p.n;
+  r.seq = p.seq;
+  return r;
+}
+
+// Cross-CTA reduce: every CTA deposits its Best, the last one to arrive (ticket) folds them.
+// Returns true in the last CTA only, with `b` = grid-wide result.  gridDim.x == 1 skips the
+// round trip through global memory.
+template <typename Key>
+__device__ __forceinline__ bool grid_reduce(const ScanParams& p, Best<Key>& b, Best<Key>* smem,
+                                            uint32_t* s_is_last) {
+  if (gridDim.x == 1) return true;
+  Best<Key>* partials = reinterpret_cast<Best<Key>*>(p.partials);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = b;
+    __threadfence();
+    const uint32_t ticket = atomicInc(p.ticket, gridDim.x - 1);  // wraps to 0: reusable
+    *s_is_last = (ticket == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!*s_is_last) return false;
+  __threadfence();
+  Best<Key> g;
+  g.clear();
+  for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    Best<Key> o;
+    const Best<Key>* src = partials + i;
+    o.kmin = __ldcg(&src->kmin);
+    o.kmax = __ldcg(&src->kmax);
+    o.pmin = __ldcg(&src->pmin);
+    o.pmax = __ldcg(&src->pmax);
+    o.pnan = __ldcg(&src->pnan);
+    g.merge(o);
+  }
+  b = block_reduce(g, smem);
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// Small inputs (a few MB): latency, not bandwidth, is what a caller sees.  One pass with
+// exact per-element (key, index) tracking -- no tile bookkeeping, no second phase: each CTA
+// takes a contiguous slice, CTA reduce, ticket, the last CTA folds the partials and
+// publishes.  The dependent chain is load -> reduce -> ticket -> fold -> publish.
+// ---------------------------------------------------------------------------------------
+template <class P>
+__global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const ScanParams p) {
+  using Key = typename P::Key;
+  constexpr int VEC = 16, NW = 4, UN = 4;
+  constexpr int VE = VEC / sizeof(typename P::Elem);
+  __shared__ Best<Key> smem[32];
+  __shared__ uint32_t s_is_last;
+  const uint8_t* main_base = p.base + p.head_elems * sizeof(typename P::Elem);
+  // contiguous slice of whole vectors per CTA, coalesced 128-bit loads, UN in flight
+  const uint64_t per = (p.n_vec + gridDim.x - 1) / gridDim.x;
+  const uint64_t vb = per * blockIdx.x;
+  uint64_t ve = vb + per;
+  ve = ve < p.n_vec ? ve : p.n_vec;
+  Best<Key> x;
+  x.clear();
+  for (uint64_t v0 = vb + threadIdx.x; v0 < ve; v0 += (uint64_t)UN * blockDim.x) {
+    uint32_t w[UN][NW];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
+      if (vi < ve) VecLoad<VEC>::ld(main_base + vi * VEC, w[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
+      if (vi < ve) {
+        const uint64_t i0 = p.head_elems + vi * VE;
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          Key k;
+          bool valid, is_nan;
+          P::classify(vec_elem<P, NW>(w[u], e), k, valid, is_nan);
+          // indices ascend within a thread: a strict compare keeps the first occurrence
+          if (valid && (k < x.kmin || x.pmin == POS_NONE)) {
+            x.kmin = k;
+            x.pmin = i0 + e;
+          }
+          if (valid && (k > x.kmax || x.pmax == POS_NONE)) {
+            x.kmax = k;
+            x.pmax = i0 + e;
+          }
+          if (P::TRACK_NAN && is_nan && x.pnan == POS_NONE) x.pnan = i0 + e;
+        }
+      }
+    }
+  }
+  // unaligned head / sub-vector tail (< 16 B each): lexicographic merges, any order
+  if (blockIdx.x == 0) exact_range<P, false>(p.base, 0, p.head_elems, x);
+  if (blockIdx.x == gridDim.x - 1) exact_range<P, false>(p.base, p.tail_start, p.n, x);
+  x = block_reduce(x, smem);
+  if (!grid_reduce(p, x, smem, &s_is_last)) return;
+  if (threadIdx.x == 0) publish_record(p, make_record(p, x));
+}
+
+template <class P, int VEC, int U, bool PREFETCH, int HINT>
+__global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanParams p) {
+  using VL = VecLoad<VEC, HINT>;
+  using Key = typename P::Key;
+  constexpr int NW = VL::NW;
   constexpr uint32_t VEC_ELEMS = VEC / sizeof(typename P::Elem);
   __shared__ Best<Key> smem[32];
   __shared__ uint32_t s_is_last;
@@ -240,14 +461,14 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
       if (t < nft) {
         const uint8_t* q = lane_base + (uint64_t)t * tile_bytes;
 #pragma unroll
-        for (int j = 0; j < U; ++j) VecLoad<VEC>::ld(q + j * jstride, a[j]);
+        for (int j = 0; j < U; ++j) VL::ld(q + j * jstride, a[j]);
       }
       while (t < nft) {
         const uint32_t t1 = t + gridDim.x;
         if (t1 < nft) {
           const uint8_t* q = lane_base + (uint64_t)t1 * tile_bytes;
 #pragma unroll
-          for (int j = 0; j < U; ++j) VecLoad<VEC>::ld(q + j * jstride, b[j]);
+          for (int j = 0; j < U; ++j) VL::ld(q + j * jstride, b[j]);
         }
         fold_tile<P, NW, U>(a, t + 1, run);
         if (t1 >= nft) break;
@@ -255,7 +476,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
         if (t2 < nft) {
           const uint8_t* q = lane_base + (uint64_t)t2 * tile_bytes;
 #pragma unroll
-          for (int j = 0; j < U; ++j) VecLoad<VEC>::ld(q + j * jstride, a[j]);
+          for (int j = 0; j < U; ++j) VL::ld(q + j * jstride, a[j]);
         }
         fold_tile<P, NW, U>(b, t1 + 1, run);
         t = t2;
@@ -264,7 +485,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
       for (; t < nft; t += gridDim.x) {
         const uint8_t* q = lane_base + (uint64_t)t * tile_bytes;
 #pragma unroll
-        for (int j = 0; j < U; ++j) VecLoad<VEC>::ld(q + j * jstride, a[j]);
+        for (int j = 0; j < U; ++j) VL::ld(q + j * jstride, a[j]);
         fold_tile<P, NW, U>(a, t + 1, run);
       }
     }
@@ -274,11 +495,11 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
     uint32_t cur[U][NW];
     const uint8_t* q =
         main_base + (uint64_t)p.n_full_tiles * tile_bytes + (uint64_t)threadIdx.x * VEC;
-    VecLoad<VEC>::ld(q, cur[0]);
+    VL::ld(q, cur[0]);
 #pragma unroll
     for (int j = 1; j < U; ++j) {
       if ((uint32_t)j * blockDim.x + threadIdx.x < p.rem_vecs) {
-        VecLoad<VEC>::ld(q + (uint64_t)j * blockDim.x * VEC, cur[j]);
+        VL::ld(q + (uint64_t)j * blockDim.x * VEC, cur[j]);
       } else {  // duplicates are neutral for a value-only min/max
 #pragma unroll
         for (int w = 0; w < NW; ++w) cur[j][w] = cur[0][w];
@@ -297,37 +518,14 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   b = block_reduce(b, smem);
 
   // ------------------------------------------- last-block-done grid finalise
-  Best<Key>* partials = reinterpret_cast<Best<Key>*>(p.partials);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = b;
-    __threadfence();
-    const uint32_t ticket = atomicInc(p.ticket, gridDim.x - 1);  // wraps to 0: reusable
-    s_is_last = (ticket == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-
-  Best<Key> g;
-  g.clear();
-  for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
-    Best<Key> o;
-    const Best<Key>* src = partials + i;
-    o.kmin = __ldcg(&src->kmin);
-    o.kmax = __ldcg(&src->kmax);
-    o.pmin = __ldcg(&src->pmin);
-    o.pmax = __ldcg(&src->pmax);
-    o.pnan = __ldcg(&src->pnan);
-    g.merge(o);
-  }
-  g = block_reduce(g, smem);
+  if (!grid_reduce(p, b, smem, &s_is_last)) return;
+  const Best<Key> g = b;
 
   // ------------------- exact (key, index) scan of the few candidate ranges
-  const uint64_t tile_elems = (uint64_t)tile_vecs * VEC_ELEMS;
   Best<Key> x;
   x.clear();
-  exact_range<P>(p.base, 0, p.head_elems, x);
-  exact_range<P>(p.base, p.tail_start, p.n, x);
+  exact_range<P, false>(p.base, 0, p.head_elems, x);
+  exact_range<P, false>(p.base, p.tail_start, p.n, x);
   const uint64_t cand[3] = {g.pmin, g.pmax, g.pnan};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -335,39 +533,11 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
     if (tid == POS_NONE) continue;
     if (c == 1 && tid == cand[0]) continue;
     if (c == 2 && (tid == cand[0] || tid == cand[1])) continue;
-    const uint64_t begin = p.head_elems + (tid - 1) * tile_elems;
-    uint64_t end = begin + tile_elems;
-    end = end < p.tail_start ? end : p.tail_start;
-    exact_range<P>(p.base, begin, end, x);
+    exact_tile<P, VEC, U>(main_base, p.head_elems, tid - 1, p.n_vec, x);
   }
   x = block_reduce(x, smem);
 
-  if (threadIdx.x == 0) {
-    amm_record r;
-    const bool has_value = x.pmin != POS_NONE;
-    const bool has_nan = x.pnan != POS_NONE;
-    r.min_key = has_value ? (int64_t)x.kmin : 0;
-    r.max_key = has_value ? (int64_t)x.kmax : 0;
-    r.min_idx = has_value ? x.pmin + p.global_offset : AMM_NO_INDEX;
-    r.max_idx = has_value ? x.pmax + p.global_offset : AMM_NO_INDEX;
-    r.nan_idx = has_nan ? x.pnan + p.global_offset : AMM_NO_INDEX;
-    r.flags = (has_value ? AMM_REC_HAS_VALUE : 0ull) | (has_nan ? AMM_REC_HAS_NAN : 0ull);
-    r.n = p.n;
-    r.seq = p.seq;
-    *p.rec_dev = r;
-    if (p.rec_host != nullptr) {
-      volatile amm_record* h = p.rec_host;
-      h->min_key = r.min_key;
-      h->min_idx = r.min_idx;
-      h->max_key = r.max_key;
-      h->max_idx = r.max_idx;
-      h->nan_idx = r.nan_idx;
-      h->flags = r.flags;
-      h->n = r.n;
-      __threadfence_system();
-      h->seq = r.seq;
-    }
-  }
+  if (threadIdx.x == 0) publish_record(p, make_record(p, x));
 }
 
 }  // namespace amm

@@ -1,0 +1,109 @@
+// scan_launch.cuh -- host-side launch geometry for the scan kernels (included by the
+// per-policy-group translation units, scan_inst.cu).
+#pragma once
+#include "amm_internal.h"
+#include "scan_kernel.cuh"
+
+namespace amm {
+
+// Load shapes compiled for every policy.  {VEC bytes, U vectors per thread per tile,
+// software prefetch}.  Tile = threads * U * VEC bytes.
+struct VariantDesc {
+  int vec, u, prefetch, hint;
+  const char* name;
+};
+static const VariantDesc kVariants[] __attribute__((unused)) = {
+    {16, 4, 1, 2, "v16x4_pf"},       // 0: 128-bit loads, 64 B/thread/tile, 2 tiles in flight
+    {32, 2, 1, 2, "v32x2_pf"},       // 1: 256-bit loads, 64 B/thread/tile, 2 tiles in flight
+    {32, 4, 1, 2, "v32x4_pf"},       // 2: 256-bit loads, 128 B/thread/tile, 2 tiles in flight
+    {16, 8, 0, 2, "v16x8"},          // 3: 128-bit loads, 128 B/thread/tile, no prefetch
+    {32, 4, 0, 2, "v32x4"},          // 4: 256-bit loads, 128 B/thread/tile, no prefetch
+    {16, 2, 1, 2, "v16x2_pf"},       // 5: small tiles
+    {16, 2, 1, 0, "v16x2_pf_nohint"},  // 6: as 5 without the L2 prefetch-size hint
+    {16, 2, 1, 1, "v16x2_pf_l2_128"},  // 7: as 5 with .L2::128B
+    {32, 1, 1, 2, "v32x1_pf"},       // 8: one 256-bit load per thread per tile
+    {16, 4, 1, 0, "v16x4_pf_nohint"},  // 9: as 0 without the hint
+};
+constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+
+template <class P, int VEC, int U, bool PF, int HINT>
+static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
+                      cudaStream_t stream) {
+  auto kernel = argminmax_scan_kernel<P, VEC, U, PF, HINT>;
+  int& occ = ws->occupancy[dtype_slot][variant];
+  if (occ == 0) {
+    int o = 0;
+    AMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, ws->threads, 0));
+    occ = o < 1 ? 1 : o;
+  }
+  const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
+  const uint64_t tile_vecs = (uint64_t)ws->threads * U;
+  // geometry: unaligned head | whole vectors | sub-vector tail
+  const uint64_t addr = (uint64_t)(uintptr_t)p.base;
+  uint64_t head = ((VEC - (addr % VEC)) % VEC) / sizeof(typename P::Elem);
+  if (head > p.n) head = p.n;
+  p.head_elems = head;
+  p.n_vec = (p.n - head) / vec_elems;
+  p.tail_start = head + p.n_vec * vec_elems;
+  const uint64_t full = p.n_vec / tile_vecs;
+  if (full >= 0xFFFFFFFEull) return AMM_ERR_TOO_LARGE;
+  p.n_full_tiles = (uint32_t)full;
+  p.rem_vecs = (uint32_t)(p.n_vec % tile_vecs);
+  const uint64_t tiles = full + (p.rem_vecs ? 1 : 0);
+  int per_sm = ws->ctas_per_sm < occ ? ws->ctas_per_sm : occ;
+  uint64_t grid = (uint64_t)ws->sm_count * (uint64_t)per_sm;
+  if (grid > tiles) grid = tiles;
+  if (grid < 1) grid = 1;
+  if (grid > (uint64_t)ws->max_grid) grid = (uint64_t)ws->max_grid;
+  kernel<<<(unsigned)grid, ws->threads, 0, stream>>>(p);
+  AMM_CUDA(cudaGetLastError());
+  ws->last_grid = (int)grid;
+  ws->last_threads = ws->threads;
+  ws->launches += 1;
+  return AMM_OK;
+}
+
+// Latency path for small inputs: one exact pass, see argminmax_direct_kernel.
+template <class P>
+static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) {
+  constexpr uint64_t VEC = 16;
+  const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
+  const uint64_t addr = (uint64_t)(uintptr_t)p.base;
+  uint64_t head = ((VEC - (addr % VEC)) % VEC) / sizeof(typename P::Elem);
+  if (head > p.n) head = p.n;
+  p.head_elems = head;
+  p.n_vec = (p.n - head) / vec_elems;
+  p.tail_start = head + p.n_vec * vec_elems;
+  const int threads = ws->direct_threads;
+  const uint64_t per_cta = (uint64_t)threads * 4;  // vectors per CTA per trip
+  uint64_t grid = (p.n_vec + per_cta - 1) / per_cta;
+  const uint64_t cap = (uint64_t)ws->sm_count * (uint64_t)ws->direct_ctas_per_sm;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  argminmax_direct_kernel<P><<<(unsigned)grid, threads, 0, stream>>>(p);
+  AMM_CUDA(cudaGetLastError());
+  ws->last_grid = (int)grid;
+  ws->last_threads = threads;
+  ws->launches += 1;
+  return AMM_OK;
+}
+
+template <class P>
+static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStream_t stream) {
+  if (p.n * sizeof(typename P::Elem) <= ws->direct_bytes) return launch_direct<P>(ws, p, stream);
+  switch (ws->variant) {
+    case 0: return launch_one<P, 16, 4, true, 2>(ws, p, dtype_slot, 0, stream);
+    case 1: return launch_one<P, 32, 2, true, 2>(ws, p, dtype_slot, 1, stream);
+    case 2: return launch_one<P, 32, 4, true, 2>(ws, p, dtype_slot, 2, stream);
+    case 3: return launch_one<P, 16, 8, false, 2>(ws, p, dtype_slot, 3, stream);
+    case 4: return launch_one<P, 32, 4, false, 2>(ws, p, dtype_slot, 4, stream);
+    case 5: return launch_one<P, 16, 2, true, 2>(ws, p, dtype_slot, 5, stream);
+    case 6: return launch_one<P, 16, 2, true, 0>(ws, p, dtype_slot, 6, stream);
+    case 7: return launch_one<P, 16, 2, true, 1>(ws, p, dtype_slot, 7, stream);
+    case 8: return launch_one<P, 32, 1, true, 2>(ws, p, dtype_slot, 8, stream);
+    case 9: return launch_one<P, 16, 4, true, 0>(ws, p, dtype_slot, 9, stream);
+    default: return AMM_ERR_ARG;
+  }
+}
+
+}  // namespace amm

@@ -191,8 +191,8 @@ int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptr
       AMM_CUDA(cudaStreamSynchronize(sh->streams[g]));
       if (shard_lens[g] == 0)
         memset(&local[g], 0, sizeof(amm_record));
-      else
-        local[g] = *sh->ws[g]->rec_host;
+      else if (!read_host_slot(sh->ws[g], sh->ws[g]->seq, &local[g]))
+        return AMM_ERR_CUDA;
     }
     table = local;
   }

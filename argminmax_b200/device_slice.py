@@ -58,6 +58,10 @@ class Workspace:
         check(lib().amm_workspace_set_tuning(self._h, threads, ctas_per_sm, variant),
               "amm_workspace_set_tuning")
 
+    def set_direct_threshold(self, nbytes: int):
+        check(lib().amm_workspace_set_direct_threshold(self._h, nbytes),
+              "amm_workspace_set_direct_threshold")
+
     def get_tuning(self) -> dict:
         t, c, v, s = (ctypes.c_int() for _ in range(4))
         check(lib().amm_workspace_get_tuning(self._h, t, c, v, s), "amm_workspace_get_tuning")

@@ -203,6 +203,15 @@ int amm_sharded_uses_nccl(const amm_sharded* sh);
 /* the per-device workspace of shard g (e.g. to apply amm_workspace_set_tuning) */
 int amm_sharded_workspace(amm_sharded* sh, int g, amm_workspace** ws);
 
+/* ------------------------------------------------------ device memory helpers */
+/* What `DeviceSlice::<T>::from_slice(&[T])` needs so that a binding does not have to link the
+   CUDA runtime itself: allocate / free HBM on `device`, blocking copies in both directions. */
+int amm_device_count(int* count);
+int amm_device_alloc(int device, size_t bytes, void** dev_ptr);
+int amm_device_free(int device, void* dev_ptr);
+int amm_copy_to_device(int device, void* dst_dev, const void* src_host, size_t bytes);
+int amm_copy_to_host(int device, void* dst_host, const void* src_dev, size_t bytes);
+
 /* ------------------------------------------------------------- diagnostics */
 const char* amm_status_string(int status);
 int amm_last_cuda_error(void);        /* cudaError_t of the last AMM_ERR_CUDA on this thread */
@@ -214,6 +223,9 @@ int amm_version(void);                /* AMM_VERSION_MAJOR * 100 + AMM_VERSION_M
    variant: load shape, see amm_variant_name().  threads / ctas_per_sm <= 0 and
    variant < 0 keep the current value. */
 int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, int variant);
+/* Inputs of at most `bytes` take the one-pass latency kernel (exact per-element tracking, no
+   second phase) instead of the streaming kernel; 0 disables it. */
+int amm_workspace_set_direct_threshold(amm_workspace* ws, uint64_t bytes);
 int amm_workspace_get_tuning(const amm_workspace* ws, int* threads, int* ctas_per_sm, int* variant,
                              int* sm_count);
 int amm_variant_count(void);

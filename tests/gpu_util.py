@@ -56,9 +56,31 @@ def run_gpu(ds, mode: int):
     return ds.nanargminmax() if mode == 1 else ds.argminmax()
 
 
-def assert_parity(arr: np.ndarray, mode: int, byte_offset: int = 0, what: str = ""):
+_path_ws = {}
+
+
+def _workspace_for(path: str):
+    """'default': size-based choice; 'stream': always the streaming (tile) kernel;
+    'direct': always the one-pass latency kernel."""
+    from argminmax_b200 import Workspace
+    if path not in _path_ws:
+        ws = Workspace(0)
+        if path == "stream":
+            ws.set_direct_threshold(0)
+        elif path == "direct":
+            ws.set_direct_threshold(1 << 62)
+        _path_ws[path] = ws
+    return _path_ws[path]
+
+
+def assert_parity(arr: np.ndarray, mode: int, byte_offset: int = 0, what: str = "",
+                  paths=("default", "stream", "direct")):
     ds, _keep = to_device(arr, byte_offset)
-    got = run_gpu(ds, mode)
     exp = oracle.argminmax(arr, mode)
-    assert got == exp, f"{what} dtype={arr.dtype} n={arr.size} mode={mode} off={byte_offset}: gpu {got} != oracle {exp}"
+    got = None
+    for path in paths:
+        ds._ws = _workspace_for(path)
+        got = run_gpu(ds, mode)
+        assert got == exp, (f"{what} dtype={arr.dtype} n={arr.size} mode={mode} off={byte_offset} "
+                            f"path={path}: gpu {got} != oracle {exp}")
     return got

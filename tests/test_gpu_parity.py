@@ -258,3 +258,17 @@ def test_split_phase_and_record():
     assert rec.n == a.size and rec.flags == 1 and rec.nan_idx == 2**64 - 1
     assert rec.min_idx == got[0] and rec.max_idx == got[1]
     ws.close()
+
+
+def test_cpp_device_slice_mirror():
+    """The C++ mirror of the trait surface (include/argminmax_b200.hpp) through a plain-g++
+    host program: the reference's doc examples and known answers (tests/cpp)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "bin", "device_slice_demo")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "tests", "cpp")], check=True)
+    proc = subprocess.run([exe, "check"], capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    assert proc.stdout.startswith("OK ")

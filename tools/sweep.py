@@ -41,12 +41,17 @@ def main():
     ap.add_argument("--threads", default="128,256,512")
     ap.add_argument("--ctas", default="1,2,3,4,6,8")
     ap.add_argument("--out", default="")
+    ap.add_argument("--rotate", type=int, default=1,
+                    help="cycle through R distinct copies of the input (R x bytes > L2 => cold)")
     a = ap.parse_args()
     lib = amm.lib()
     data = make_data(a.dtype, a.n)
     ws = amm.Workspace(0)
-    ds = amm.DeviceSlice.from_torch(data, dtype=a.dtype, workspace=ws,
-                                    stream=torch.cuda.current_stream().cuda_stream)
+    ws.set_direct_threshold(0)  # this tool sweeps the streaming kernel only
+    copies = [data] + [data.clone() for _ in range(a.rotate - 1)]
+    dss = [amm.DeviceSlice.from_torch(c, dtype=a.dtype, workspace=ws,
+                                      stream=torch.cuda.current_stream().cuda_stream) for c in copies]
+    ds = dss[0]
     nbytes = a.n * amm.DTYPE_SIZE[a.dtype]
     variants = [int(v) for v in a.variants.split(",")] if a.variants else range(lib.amm_variant_count())
     rows = []
@@ -63,8 +68,8 @@ def main():
                 assert res == ref, (res, ref)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                for _ in range(a.iters):
-                    ds.launch(a.mode)
+                for it in range(a.iters):
+                    dss[it % len(dss)].launch(a.mode)
                 e1.record()
                 e1.synchronize()
                 ms = e0.elapsed_time(e1) / a.iters
