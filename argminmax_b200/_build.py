@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
 ]
-OBJ_DIR = os.path.join(HERE, "lib", "obj")
+OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "obj")  # build/ is git- and gpurun-ignored
 
 
 def _nvcc() -> str:

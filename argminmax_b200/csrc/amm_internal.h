@@ -28,13 +28,16 @@ constexpr int AMM_MAX_VARIANTS = 16;
 struct amm_workspace {
   int device;
   int sm_count;
+  // streaming-kernel geometry; 0 / 0 / -1 = automatic (chosen per call from the input size)
   int threads;      // CTA size
   int ctas_per_sm;  // persistent CTAs per SM (capped by occupancy)
-  int variant;      // load shape, see kVariants in libamm.cu
+  int variant;      // load shape, see kVariants in scan_launch.cuh
+  int eff_threads, eff_ctas_per_sm, eff_variant;  // what the last streaming launch used
   int max_grid;
   uint64_t direct_bytes;  // inputs up to this size take the one-pass latency kernel
   int direct_threads, direct_ctas_per_sm;
-  int occupancy[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // cached per current `threads`
+  int occupancy[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];      // cached CTAs/SM ...
+  int occupancy_threads[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // ... for this CTA size
   void* partials;            // max_grid x 64 B
   uint32_t* ticket;          // last-block-done counter (self-resetting)
   amm_record* rec_dev;       // device record slot

@@ -226,10 +226,10 @@ int amm_workspace_create(int device, amm_workspace** out) {
   cudaDeviceProp prop;
   AMM_CUDA(cudaGetDeviceProperties(&prop, device));
   ws->sm_count = prop.multiProcessorCount;
-  ws->threads = 512;
-  ws->ctas_per_sm = 2;
-  ws->variant = 0;
-  ws->direct_bytes = (uint64_t)1 << 20;
+  ws->threads = 0;      // automatic
+  ws->ctas_per_sm = 0;  // automatic
+  ws->variant = -1;     // automatic
+  ws->direct_bytes = (uint64_t)8 << 20;
   ws->direct_threads = 256;
   ws->direct_ctas_per_sm = 2;
   if (getenv("AMM_DIRECT_BYTES")) ws->direct_bytes = strtoull(getenv("AMM_DIRECT_BYTES"), nullptr, 10);
@@ -429,19 +429,12 @@ int amm_version(void) { return AMM_VERSION_MAJOR * 100 + AMM_VERSION_MINOR; }
 
 int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, int variant) {
   if (!ws) return AMM_ERR_ARG;
-  if (threads > 0) {
-    if (threads % 32 != 0 || threads < 64 || threads > MAX_THREADS) return AMM_ERR_ARG;
-    if (threads != ws->threads) memset(ws->occupancy, 0, sizeof(ws->occupancy));
-    ws->threads = threads;
-  }
-  if (ctas_per_sm > 0) {
-    if (ctas_per_sm > 32) return AMM_ERR_ARG;
-    ws->ctas_per_sm = ctas_per_sm;
-  }
-  if (variant >= 0) {
-    if (variant >= kNumVariants) return AMM_ERR_ARG;
-    ws->variant = variant;
-  }
+  if (threads > 0 && (threads % 32 != 0 || threads < 64 || threads > MAX_THREADS)) return AMM_ERR_ARG;
+  if (ctas_per_sm > 32) return AMM_ERR_ARG;
+  if (variant >= kNumVariants) return AMM_ERR_ARG;
+  ws->threads = threads > 0 ? threads : 0;
+  ws->ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 0;
+  ws->variant = variant >= 0 ? variant : -1;
   return AMM_OK;
 }
 
@@ -454,9 +447,9 @@ int amm_workspace_set_direct_threshold(amm_workspace* ws, uint64_t bytes) {
 int amm_workspace_get_tuning(const amm_workspace* ws, int* threads, int* ctas_per_sm, int* variant,
                              int* sm_count) {
   if (!ws) return AMM_ERR_ARG;
-  if (threads) *threads = ws->threads;
-  if (ctas_per_sm) *ctas_per_sm = ws->ctas_per_sm;
-  if (variant) *variant = ws->variant;
+  if (threads) *threads = ws->eff_threads;
+  if (ctas_per_sm) *ctas_per_sm = ws->eff_ctas_per_sm;
+  if (variant) *variant = ws->eff_variant;
   if (sm_count) *sm_count = ws->sm_count;
   return AMM_OK;
 }

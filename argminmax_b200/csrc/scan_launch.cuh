@@ -30,14 +30,16 @@ template <class P, int VEC, int U, bool PF, int HINT>
 static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
                       cudaStream_t stream) {
   auto kernel = argminmax_scan_kernel<P, VEC, U, PF, HINT>;
+  const int threads = ws->eff_threads;
   int& occ = ws->occupancy[dtype_slot][variant];
-  if (occ == 0) {
+  if (occ == 0 || ws->occupancy_threads[dtype_slot][variant] != threads) {
     int o = 0;
-    AMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, ws->threads, 0));
+    AMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, threads, 0));
     occ = o < 1 ? 1 : o;
+    ws->occupancy_threads[dtype_slot][variant] = threads;
   }
   const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
-  const uint64_t tile_vecs = (uint64_t)ws->threads * U;
+  const uint64_t tile_vecs = (uint64_t)threads * U;
   // geometry: unaligned head | whole vectors | sub-vector tail
   const uint64_t addr = (uint64_t)(uintptr_t)p.base;
   uint64_t head = ((VEC - (addr % VEC)) % VEC) / sizeof(typename P::Elem);
@@ -50,15 +52,15 @@ static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int vari
   p.n_full_tiles = (uint32_t)full;
   p.rem_vecs = (uint32_t)(p.n_vec % tile_vecs);
   const uint64_t tiles = full + (p.rem_vecs ? 1 : 0);
-  int per_sm = ws->ctas_per_sm < occ ? ws->ctas_per_sm : occ;
+  int per_sm = ws->eff_ctas_per_sm < occ ? ws->eff_ctas_per_sm : occ;
   uint64_t grid = (uint64_t)ws->sm_count * (uint64_t)per_sm;
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
   if (grid > (uint64_t)ws->max_grid) grid = (uint64_t)ws->max_grid;
-  kernel<<<(unsigned)grid, ws->threads, 0, stream>>>(p);
+  kernel<<<(unsigned)grid, threads, 0, stream>>>(p);
   AMM_CUDA(cudaGetLastError());
   ws->last_grid = (int)grid;
-  ws->last_threads = ws->threads;
+  ws->last_threads = threads;
   ws->launches += 1;
   return AMM_OK;
 }
@@ -90,8 +92,16 @@ static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) 
 
 template <class P>
 static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStream_t stream) {
-  if (p.n * sizeof(typename P::Elem) <= ws->direct_bytes) return launch_direct<P>(ws, p, stream);
-  switch (ws->variant) {
+  const uint64_t bytes = p.n * sizeof(typename P::Elem);
+  if (bytes <= ws->direct_bytes) return launch_direct<P>(ws, p, stream);
+  // Automatic geometry (B200 sweeps, profiles/r01_sweeps.md): 256-bit loads and a deep grid
+  // win on HBM-sized inputs; below ~0.5 GiB the fixed tail matters more and 128-bit loads
+  // with 2 CTAs/SM finish sooner.
+  const bool big = bytes >= ((uint64_t)512 << 20);
+  ws->eff_variant = ws->variant >= 0 ? ws->variant : (big ? 1 : 0);
+  ws->eff_threads = ws->threads > 0 ? ws->threads : 256;
+  ws->eff_ctas_per_sm = ws->ctas_per_sm > 0 ? ws->ctas_per_sm : (big ? 8 : 2);
+  switch (ws->eff_variant) {
     case 0: return launch_one<P, 16, 4, true, 2>(ws, p, dtype_slot, 0, stream);
     case 1: return launch_one<P, 32, 2, true, 2>(ws, p, dtype_slot, 1, stream);
     case 2: return launch_one<P, 32, 4, true, 2>(ws, p, dtype_slot, 2, stream);

@@ -218,10 +218,11 @@ int amm_last_cuda_error(void);        /* cudaError_t of the last AMM_ERR_CUDA on
 size_t amm_dtype_size(int dtype);     /* bytes per element, 0 for an unknown dtype */
 int amm_version(void);                /* AMM_VERSION_MAJOR * 100 + AMM_VERSION_MINOR */
 
-/* Scan geometry knobs (benchmarks / tuning only; defaults are the tuned values).
-   threads: CTA size (multiple of 32, 64..1024); ctas_per_sm: persistent CTAs per SM;
-   variant: load shape, see amm_variant_name().  threads / ctas_per_sm <= 0 and
-   variant < 0 keep the current value. */
+/* Scan geometry knobs (benchmarks / tuning only).  By default the library picks the geometry
+   per call from the input size.  threads: CTA size (multiple of 32, 64..512); ctas_per_sm:
+   persistent CTAs per SM; variant: load shape, see amm_variant_name().  threads /
+   ctas_per_sm <= 0 and variant < 0 select "automatic" for that knob.  get_tuning reports what
+   the most recent streaming launch actually used. */
 int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, int variant);
 /* Inputs of at most `bytes` take the one-pass latency kernel (exact per-element tracking, no
    second phase) instead of the streaming kernel; 0 disables it. */
