@@ -18,7 +18,7 @@ FLOAT_DTYPES = ("f16", "f32", "f64")
 IGNORE_NAN = 0
 RETURN_NAN = 1
 
-AMM_OK, AMM_ERR_EMPTY, AMM_ERR_ARG, AMM_ERR_ALIGN, AMM_ERR_CUDA, AMM_ERR_NCCL, AMM_ERR_TOO_LARGE = range(7)
+AMM_OK, AMM_ERR_EMPTY, AMM_ERR_ARG, AMM_ERR_ALIGN, AMM_ERR_CUDA, AMM_ERR_NCCL, AMM_ERR_TOO_LARGE, AMM_ERR_PEER = range(8)
 
 
 class AmmRecord(ctypes.Structure):
@@ -63,6 +63,11 @@ SIGNATURES = {
     "amm_workspace_device_record": (_i, [_vp, ctypes.POINTER(_vp)]),
     "amm_workspace_host_record": (_i, [_vp, ctypes.POINTER(ctypes.POINTER(AmmRecord))]),
     "amm_combine_records": (_i, [ctypes.POINTER(AmmRecord), _i, _i, _u64p]),
+    "amm_exchange_create": (_i, [_vp, _i, _i, _vp]),
+    "amm_exchange_connect_ipc": (_i, [_vp, _vp]),
+    "amm_exchange_connect_ptrs": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "amm_exchange_local_buffer": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "amm_argminmax_launch_exchange": (_i, [_i, _vp, _u64, _i, _u64, _vp, _vp]),
     "amm_host_argminmax": (_i, [_i, _vp, _u64, _i, _vp, _u64p]),
     "amm_host_argminmax_record": (_i, [_i, _vp, _u64, _i, _u64, _vp, ctypes.POINTER(AmmRecord)]),
     "amm_combine_records_launch": (_i, [_vp, _i, _i, _vp, _vp]),
@@ -70,6 +75,7 @@ SIGNATURES = {
     "amm_sharded_destroy": (_i, [_vp]),
     "amm_sharded_argminmax": (_i, [_vp, _i, ctypes.POINTER(_vp), _u64p, _i, _u64p]),
     "amm_sharded_uses_nccl": (_i, [_vp]),
+    "amm_sharded_uses_peer_exchange": (_i, [_vp]),
     "amm_sharded_workspace": (_i, [_vp, _i, ctypes.POINTER(_vp)]),
     "amm_device_count": (_i, [ctypes.POINTER(_i)]),
     "amm_device_alloc": (_i, [_i, ctypes.c_size_t, ctypes.POINTER(_vp)]),

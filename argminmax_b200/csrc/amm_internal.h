@@ -48,12 +48,19 @@ struct amm_workspace {
   int last_grid, last_threads;
   uint64_t launches;
   amm_host_pipeline* pipe;  // lazily created by amm_host_argminmax
+  // fused cross-GPU exchange (amm_exchange_*): this rank's buffer, the peer pointer table
+  int xworld, xrank;
+  uint64_t* xbuf;            // cudaMalloc'ed, 2 parities x world slots x 128 B
+  uint64_t** xpeers_dev;     // device array [world] of peer-mapped buffer pointers
+  void* xopened[16];         // pointers obtained from cudaIpcOpenMemHandle (to close)
+  uint64_t xseq;
 };
 
 namespace amm {
 int set_device(int device);
 int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global_offset,
-           amm_workspace* ws, cudaStream_t stream, void* dev_record_out);
+           amm_workspace* ws, cudaStream_t stream, void* dev_record_out, bool exchange = false);
+void exchange_destroy(amm_workspace* ws);
 bool read_host_slot(const amm_workspace* ws, uint64_t want, amm_record* out);
 void combine(const amm_record* recs, int count, int mode, uint64_t out[2]);
 amm_record fold_records(const amm_record* recs, int count);

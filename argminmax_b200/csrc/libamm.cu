@@ -86,11 +86,18 @@ int set_device(int device) {
 }
 
 int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global_offset,
-           amm_workspace* ws, cudaStream_t stream, void* dev_record_out) {
-  if (ws == nullptr || dev_ptr == nullptr) return AMM_ERR_ARG;
+           amm_workspace* ws, cudaStream_t stream, void* dev_record_out, bool exchange) {
+  if (ws == nullptr) return AMM_ERR_ARG;
   if (dtype < 0 || dtype >= AMM_DTYPE_COUNT) return AMM_ERR_ARG;
   if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
-  if (n == 0) return AMM_ERR_EMPTY;
+  if (exchange) {
+    // an empty shard still takes part in the exchange (it contributes "no value")
+    if (ws->xworld < 2 || !ws->xpeers_dev) return AMM_ERR_ARG;
+    if (n != 0 && dev_ptr == nullptr) return AMM_ERR_ARG;
+  } else {
+    if (dev_ptr == nullptr) return AMM_ERR_ARG;
+    if (n == 0) return AMM_ERR_EMPTY;
+  }
   const size_t es = amm_dtype_size(dtype);
   if (((uintptr_t)dev_ptr) % es != 0) return AMM_ERR_ALIGN;
   int rc = set_device(ws->device);
@@ -107,7 +114,25 @@ int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global
   p.seq = ++ws->seq;
   p.mode = mode;
   p.publish_fence = ws->publish_fence;
+  if (exchange) {
+    p.world = ws->xworld;
+    p.rank = ws->xrank;
+    p.peer_slots = ws->xpeers_dev;
+    p.xseq = ++ws->xseq;
+  }
   return dispatch(ws, dtype, mode, p, stream);
+}
+
+void exchange_destroy(amm_workspace* ws) {
+  for (int i = 0; i < 16; ++i) {
+    if (ws->xopened[i]) cudaIpcCloseMemHandle(ws->xopened[i]);
+    ws->xopened[i] = nullptr;
+  }
+  if (ws->xpeers_dev) cudaFree(ws->xpeers_dev);
+  if (ws->xbuf) cudaFree(ws->xbuf);
+  ws->xpeers_dev = nullptr;
+  ws->xbuf = nullptr;
+  ws->xworld = 0;
 }
 
 // Fold records (ascending shard order) into one record.  Strict compares on the key,
@@ -255,6 +280,7 @@ int amm_workspace_destroy(amm_workspace* ws) {
   if (!ws) return AMM_OK;
   set_device(ws->device);
   host_pipeline_destroy(ws);
+  exchange_destroy(ws);
   if (ws->partials) cudaFree(ws->partials);
   if (ws->ticket) cudaFree(ws->ticket);
   if (ws->rec_dev) cudaFree(ws->rec_dev);
@@ -267,6 +293,76 @@ int amm_argminmax_launch(int dtype, const void* dev_ptr, uint64_t n, int mode,
                          uint64_t global_offset, amm_workspace* ws, void* stream,
                          void* dev_record_out) {
   return launch(dtype, dev_ptr, n, mode, global_offset, ws, (cudaStream_t)stream, dev_record_out);
+}
+
+/* ---- fused cross-GPU exchange: setup ------------------------------------------------- */
+int amm_exchange_create(amm_workspace* ws, int world, int rank, void* ipc_handle_out) {
+  if (!ws || world < 2 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return AMM_ERR_ARG;
+  int rc = set_device(ws->device);
+  if (rc) return rc;
+  exchange_destroy(ws);
+  const size_t bytes = (size_t)2 * world * XCHG_SLOT_WORDS * sizeof(uint64_t);
+  AMM_CUDA(cudaMalloc((void**)&ws->xbuf, bytes));
+  AMM_CUDA(cudaMemset(ws->xbuf, 0, bytes));
+  AMM_CUDA(cudaMalloc((void**)&ws->xpeers_dev, sizeof(uint64_t*) * (size_t)world));
+  AMM_CUDA(cudaDeviceSynchronize());
+  ws->xworld = world;
+  ws->xrank = rank;
+  ws->xseq = 0;
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is exchanged as 64 bytes");
+    cudaIpcMemHandle_t h;
+    AMM_CUDA(cudaIpcGetMemHandle(&h, ws->xbuf));
+    memcpy(ipc_handle_out, &h, sizeof(h));
+  }
+  return AMM_OK;
+}
+
+int amm_exchange_local_buffer(amm_workspace* ws, void** dev_ptr) {
+  if (!ws || !dev_ptr || !ws->xbuf) return AMM_ERR_ARG;
+  *dev_ptr = ws->xbuf;
+  return AMM_OK;
+}
+
+static int exchange_upload(amm_workspace* ws, uint64_t** table) {
+  AMM_CUDA(cudaMemcpy(ws->xpeers_dev, table, sizeof(uint64_t*) * (size_t)ws->xworld,
+                      cudaMemcpyHostToDevice));
+  return AMM_OK;
+}
+
+int amm_exchange_connect_ipc(amm_workspace* ws, const void* ipc_handles) {
+  if (!ws || !ipc_handles || ws->xworld < 2) return AMM_ERR_ARG;
+  int rc = set_device(ws->device);
+  if (rc) return rc;
+  uint64_t* table[XCHG_MAX_WORLD];
+  for (int r = 0; r < ws->xworld; ++r) {
+    if (r == ws->xrank) {
+      table[r] = ws->xbuf;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)ipc_handles + (size_t)r * sizeof(h), sizeof(h));
+    void* ptr = nullptr;
+    AMM_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    ws->xopened[r] = ptr;
+    table[r] = (uint64_t*)ptr;
+  }
+  return exchange_upload(ws, table);
+}
+
+int amm_exchange_connect_ptrs(amm_workspace* ws, void* const* peer_buffers) {
+  if (!ws || !peer_buffers || ws->xworld < 2) return AMM_ERR_ARG;
+  int rc = set_device(ws->device);
+  if (rc) return rc;
+  uint64_t* table[XCHG_MAX_WORLD];
+  for (int r = 0; r < ws->xworld; ++r) table[r] = (uint64_t*)peer_buffers[r];
+  table[ws->xrank] = ws->xbuf;
+  return exchange_upload(ws, table);
+}
+
+int amm_argminmax_launch_exchange(int dtype, const void* dev_ptr, uint64_t n, int mode,
+                                  uint64_t global_offset, amm_workspace* ws, void* stream) {
+  return launch(dtype, dev_ptr, n, mode, global_offset, ws, (cudaStream_t)stream, nullptr, true);
 }
 
 int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2]) {
@@ -295,6 +391,7 @@ int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2
     AMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     if (!read_host_slot(ws, want, &r)) return AMM_ERR_CUDA;  // record never published
   }
+  if (r.flags & AMM_REC_PEER_TIMEOUT) return AMM_ERR_PEER;
   combine(&r, 1, mode, out);
   return AMM_OK;
 }
@@ -409,6 +506,7 @@ const char* amm_status_string(int status) {
     case AMM_ERR_CUDA: return "CUDA error (see amm_last_cuda_error)";
     case AMM_ERR_NCCL: return "NCCL error or NCCL unavailable";
     case AMM_ERR_TOO_LARGE: return "input too large";
+    case AMM_ERR_PEER: return "peer exchange timed out (a rank did not take part in the call)";
     default: return "unknown status";
   }
 }

@@ -58,7 +58,16 @@ struct ScanParams {
   uint64_t seq;
   int mode;
   int publish_fence;  // debug: also issue a system-scope fence after publishing
+  // ---- fused cross-GPU exchange (world > 1): see finalize()
+  int world;                   // ranks taking part in this logical call (1 = none)
+  int rank;                    // this GPU's position (ascending shard order)
+  uint64_t* const* peer_slots;  // device array [world]: every rank's exchange buffer, peer-mapped
+  uint64_t xseq;               // exchange sequence number, identical on all ranks
 };
+
+constexpr int XCHG_SLOT_WORDS = 16;     // 128 B per (parity, rank) slot: 8 record words,
+constexpr int XCHG_MAX_WORLD = 16;      // checksum, tag; 2 parities per buffer
+constexpr uint64_t AMM_REC_PEER_TIMEOUT = 4ull;  // record.flags bit: a peer never showed up
 
 // (key, position) candidates for min, max and first NaN.  Positions are tile ids in
 // the streaming phase and element indices in the exact phase.
@@ -336,6 +345,106 @@ __device__ __forceinline__ amm_record make_record(const ScanParams& p, const Bes
   return r;
 }
 
+// Last step of the last CTA.  world == 1: publish this GPU's record.  world > 1: the
+// compute step is FUSED with its collective -- instead of returning to the host for an NCCL
+// all-gather, the last CTA stores its 64-byte record straight into every peer's exchange
+// buffer over NVLink (peer-mapped pointers, one thread per peer), then polls its own buffer
+// until all `world` records of this call (tag == xseq, checksum valid) have landed, folds them
+// in ascending rank order with strict compares (= global first occurrence, the reference's
+// merge rule src/simd/generic.rs:513-520) and publishes the GLOBAL record.  Two parity banks
+// make back-to-back calls safe: a rank can only reach call s+2 after every peer has finished
+// reading call s.  A peer that never arrives trips a ~4 s timeout and is reported in flags.
+template <typename Key>
+__device__ __forceinline__ void finalize(const ScanParams& p, const Best<Key>& x) {
+  if (p.world <= 1) {
+    if (threadIdx.x == 0) publish_record(p, make_record(p, x));
+    return;
+  }
+  __shared__ amm_record s_mine;
+  __shared__ amm_record s_all[XCHG_MAX_WORLD];
+  __shared__ uint32_t s_timeout;
+  if (threadIdx.x == 0) {
+    s_mine = make_record(p, x);
+    s_timeout = 0;
+  }
+  __syncthreads();
+  const uint64_t bank = (p.xseq & 1ull) * (uint64_t)p.world;
+  if ((int)threadIdx.x < p.world) {
+    // push my record into peer `t`'s buffer, slot [bank + rank]
+    const int t = threadIdx.x;
+    volatile uint64_t* dst = p.peer_slots[t] + (bank + (uint64_t)p.rank) * XCHG_SLOT_WORDS;
+    const uint64_t* src = reinterpret_cast<const uint64_t*>(&s_mine);
+    uint64_t c = 0x5EEDFACE0DDBA11ull ^ p.xseq;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      dst[i] = src[i];
+      c ^= src[i];
+    }
+    dst[8] = c;
+    dst[9] = p.xseq;
+    __threadfence_system();
+    // pull peer `t`'s record out of MY buffer, slot [bank + t]
+    const volatile uint64_t* in = p.peer_slots[p.rank] + (bank + (uint64_t)t) * XCHG_SLOT_WORDS;
+    uint64_t w[10];
+    unsigned long long t0 = 0, now = 0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    bool ok = false;
+    while (!ok) {
+      if (in[9] == p.xseq) {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) w[i] = in[i];
+        uint64_t cc = 0x5EEDFACE0DDBA11ull ^ p.xseq;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cc ^= w[i];
+        ok = (cc == w[8]) && (w[9] == p.xseq);
+      }
+      if (!ok) {
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+        if (now - t0 > 4000000000ull) {  // ns
+          atomicExch(&s_timeout, 1u);
+          break;
+        }
+      }
+    }
+    uint64_t* out = reinterpret_cast<uint64_t*>(&s_all[t]);
+    if (ok) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[i] = w[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[i] = 0;  // no value, no NaN
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    amm_record o;
+    bool have = false;
+    o.min_key = o.max_key = 0;
+    o.min_idx = o.max_idx = o.nan_idx = AMM_NO_INDEX;
+    o.n = 0;
+    for (int g = 0; g < p.world; ++g) {
+      const amm_record r = s_all[g];
+      o.n += r.n;
+      if ((r.flags & AMM_REC_HAS_NAN) && r.nan_idx < o.nan_idx) o.nan_idx = r.nan_idx;
+      if (!(r.flags & AMM_REC_HAS_VALUE)) continue;
+      if (!have || r.min_key < o.min_key || (r.min_key == o.min_key && r.min_idx < o.min_idx)) {
+        o.min_key = r.min_key;
+        o.min_idx = r.min_idx;
+      }
+      if (!have || r.max_key > o.max_key || (r.max_key == o.max_key && r.max_idx < o.max_idx)) {
+        o.max_key = r.max_key;
+        o.max_idx = r.max_idx;
+      }
+      have = true;
+    }
+    o.flags = (have ? AMM_REC_HAS_VALUE : 0ull) |
+              (o.nan_idx != AMM_NO_INDEX ? AMM_REC_HAS_NAN : 0ull) |
+              (s_timeout ? AMM_REC_PEER_TIMEOUT : 0ull);
+    o.seq = p.seq;
+    publish_record(p, o);
+  }
+}
+
 // Cross-CTA reduce: every CTA deposits its Best, the last one to arrive (ticket) folds them.
 // Returns true in the last CTA only, with `b` = grid-wide result.  gridDim.x == 1 skips the
 // round trip through global memory.
@@ -426,7 +535,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
   if (blockIdx.x == gridDim.x - 1) exact_range<P, false>(p.base, p.tail_start, p.n, x);
   x = block_reduce(x, smem);
   if (!grid_reduce(p, x, smem, &s_is_last)) return;
-  if (threadIdx.x == 0) publish_record(p, make_record(p, x));
+  finalize(p, x);
 }
 
 template <class P, int VEC, int U, bool PREFETCH, int HINT>
@@ -537,7 +646,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   }
   x = block_reduce(x, smem);
 
-  if (threadIdx.x == 0) publish_record(p, make_record(p, x));
+  finalize(p, x);
 }
 
 }  // namespace amm

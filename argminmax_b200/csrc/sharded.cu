@@ -15,6 +15,7 @@
 // the host process (e.g. torch's).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -64,6 +65,7 @@ struct amm_sharded {
   amm_record* gathered[kMaxGpus];  // device, ngpu records each
   amm_record* gathered_host;       // pinned, ngpu records
   bool use_nccl;
+  bool use_peer;  // fused in-kernel exchange over peer-mapped memory (default when possible)
   NcclApi api;
   ncclComm_t comms[kMaxGpus];
 };
@@ -119,8 +121,45 @@ int amm_sharded_create(int ngpu, const int* devices, amm_sharded** out) {
     amm_sharded_destroy(sh);
     return AMM_ERR_CUDA;
   }
+  // Exchange mode: "peer" (default when every pair of devices is distinct and P2P-capable):
+  // the scan kernel's last CTA writes its record into the peers' buffers -- no NCCL call, no
+  // extra launch per call; "nccl": one ncclAllGather of the records; "host": pinned slots.
+  const char* want = getenv("AMM_SHARDED_EXCHANGE");
+  const bool allow_peer = !want || strcmp(want, "peer") == 0;
+  const bool allow_nccl = !want || strcmp(want, "nccl") == 0 || strcmp(want, "peer") == 0;
+  sh->use_peer = false;
+  if (ngpu > 1 && allow_peer) {
+    bool ok = true;
+    for (int a = 0; a < ngpu && ok; ++a)
+      for (int b = 0; b < ngpu && ok; ++b) {
+        if (a == b) continue;
+        if (sh->devices[a] == sh->devices[b]) ok = false;  // spin-waiting kernels need own GPUs
+        int can = 0;
+        if (ok && cudaDeviceCanAccessPeer(&can, sh->devices[a], sh->devices[b]) != cudaSuccess) ok = false;
+        if (!can) ok = false;
+      }
+    if (ok) {
+      for (int a = 0; a < ngpu && ok; ++a) {
+        if (set_device(sh->devices[a])) ok = false;
+        for (int b = 0; b < ngpu && ok; ++b) {
+          if (a == b) continue;
+          cudaError_t pe = cudaDeviceEnablePeerAccess(sh->devices[b], 0);
+          if (pe == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+          else if (pe != cudaSuccess) ok = false;
+        }
+        if (ok && amm_exchange_create(sh->ws[a], ngpu, a, nullptr) != AMM_OK) ok = false;
+      }
+      void* bufs[kMaxGpus];
+      for (int a = 0; a < ngpu && ok; ++a)
+        if (amm_exchange_local_buffer(sh->ws[a], &bufs[a]) != AMM_OK) ok = false;
+      for (int a = 0; a < ngpu && ok; ++a)
+        if (amm_exchange_connect_ptrs(sh->ws[a], bufs) != AMM_OK) ok = false;
+      (void)cudaGetLastError();
+      sh->use_peer = ok;
+    }
+  }
   sh->use_nccl = false;
-  if (ngpu > 1 && load_nccl(sh->api)) {
+  if (ngpu > 1 && !sh->use_peer && allow_nccl && load_nccl(sh->api)) {
     if (sh->api.CommInitAll(sh->comms, ngpu, sh->devices) == 0) {
       sh->use_nccl = true;
     } else {
@@ -132,6 +171,7 @@ int amm_sharded_create(int ngpu, const int* devices, amm_sharded** out) {
 }
 
 int amm_sharded_uses_nccl(const amm_sharded* sh) { return (sh && sh->use_nccl) ? 1 : 0; }
+int amm_sharded_uses_peer_exchange(const amm_sharded* sh) { return (sh && sh->use_peer) ? 1 : 0; }
 
 int amm_sharded_workspace(amm_sharded* sh, int g, amm_workspace** ws) {
   if (!sh || !ws || g < 0 || g >= sh->ngpu) return AMM_ERR_ARG;
@@ -145,6 +185,33 @@ int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptr
   uint64_t total = 0;
   for (int g = 0; g < sh->ngpu; ++g) total += shard_lens[g];
   if (total == 0) return AMM_ERR_EMPTY;
+  if (sh->use_peer) {
+    // fused path: one kernel per device does scan + exchange + combine
+    uint64_t off = 0;
+    for (int g = 0; g < sh->ngpu; ++g) {
+      int rc = launch(dtype, dev_ptrs[g], shard_lens[g], mode, off, sh->ws[g], sh->streams[g],
+                      nullptr, true);
+      if (rc) return rc;
+      off += shard_lens[g];
+    }
+    uint64_t first[2] = {0, 0};
+    for (int g = 0; g < sh->ngpu; ++g) {
+      uint64_t r[2];
+      int rc = set_device(sh->devices[g]);
+      if (rc) return rc;
+      rc = amm_workspace_wait(sh->ws[g], sh->streams[g], mode, r);
+      if (rc) return rc;
+      if (g == 0) {
+        first[0] = r[0];
+        first[1] = r[1];
+      } else if (r[0] != first[0] || r[1] != first[1]) {
+        return AMM_ERR_PEER;  // every device must have folded the same table
+      }
+    }
+    out[0] = first[0];
+    out[1] = first[1];
+    return AMM_OK;
+  }
   // 1. every device scans its shard (async, one stream per device)
   uint64_t offset = 0;
   for (int g = 0; g < sh->ngpu; ++g) {

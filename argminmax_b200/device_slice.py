@@ -276,6 +276,10 @@ class ShardedDeviceSlice:
     def uses_nccl(self) -> bool:
         return bool(lib().amm_sharded_uses_nccl(self._h))
 
+    @property
+    def uses_peer_exchange(self) -> bool:
+        return bool(lib().amm_sharded_uses_peer_exchange(self._h))
+
     def __len__(self):
         return sum(s.n for s in self.shards)
 

@@ -1,17 +1,22 @@
 """One rank per GPU (torch.distributed): a logical array sharded into consecutive index
 ranges over the ranks of one job.
 
-Data path per call, on the rank's compute stream, nothing synchronous in between:
+Data path per call, on the rank's compute stream, nothing synchronous in between.
+Default ("peer"): ONE kernel per rank -- the scan kernel's last CTA stores the rank's 64-byte
+record into every peer's exchange buffer over NVLink (CUDA-IPC-mapped memory), waits for the
+other ranks' records, folds them and publishes the global answer (amm_exchange_*).
+Fallback / AMM_SHARDED_EXCHANGE=nccl:
     scan kernel (64-byte record, indices already global)
  -> all_gather_into_tensor of the records   (NCCL over NVLink/NVSwitch: world x 64 B)
  -> combine kernel (ascending rank order, strict compares => first occurrence)
- -> (argmin, argmax) read from the workspace's pinned host slot.
+Either way (argmin, argmax) is read from the workspace's pinned host slot.
 torch.distributed is plumbing only (rendezvous + the collective).  With the gloo backend
 (CPU tests) the record exchange and the host-side combine are exercised without a GPU.
 """
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional
 
 from . import _ffi
@@ -72,6 +77,33 @@ class DistributedShardedSlice:
         self.n_total = int(sum(lens))
         self._rec = torch.zeros(64, dtype=torch.uint8, device=dev)
         self._gathered = torch.zeros(64 * self.world, dtype=torch.uint8, device=dev)
+        self.exchange = "nccl"
+        want = os.environ.get("AMM_SHARDED_EXCHANGE", "peer")
+        if self.world > 1 and want == "peer":
+            self._setup_peer_exchange(dev)
+
+    def _setup_peer_exchange(self, dev) -> None:
+        """Fused in-kernel exchange: allocate this rank's buffer, swap CUDA IPC handles once
+        (the only collective in the setup), map the peers' buffers.  Falls back to the NCCL
+        all-gather path if any rank cannot set it up (all ranks agree on the outcome)."""
+        import torch
+        import torch.distributed as dist
+
+        ws = self.shard.workspace
+        handle = (ctypes.c_uint8 * 64)()
+        ok = lib().amm_exchange_create(ws.handle, self.world, self.rank, handle) == _ffi.AMM_OK
+        mine = torch.tensor(list(bytes(handle)) + [1 if ok else 0], dtype=torch.uint8, device=dev)
+        allh = torch.zeros(65 * self.world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        rows = allh.view(self.world, 65).cpu()
+        ok = bool(rows[:, 64].min().item() == 1)
+        if ok:
+            table = bytes(rows[:, :64].contiguous().numpy().tobytes())
+            buf = (ctypes.c_uint8 * len(table)).from_buffer_copy(table)
+            ok = lib().amm_exchange_connect_ipc(ws.handle, buf) == _ffi.AMM_OK
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        self.exchange = "peer" if int(flag.item()) == 1 else "nccl"
 
     def __len__(self):
         return self.n_total
@@ -83,6 +115,11 @@ class DistributedShardedSlice:
 
         stream = torch.cuda.current_stream().cuda_stream
         s = self.shard
+        if self.exchange == "peer":
+            rc = lib().amm_argminmax_launch_exchange(DTYPES[s.dtype], s.data_ptr, s.n, mode,
+                                                     self.global_offset, s.workspace.handle, stream)
+            check(rc, "amm_argminmax_launch_exchange")
+            return
         if s.n == 0:
             self._rec.zero_()  # no value, no NaN
         else:

@@ -236,6 +236,8 @@ def main() -> int:
     device = torch.device("cuda", local_rank)
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=device)
     amm.lib()  # fail loudly if the extension is missing
 
@@ -395,7 +397,10 @@ def main() -> int:
                             "uniform random bit patterns NaN->0 (reference bench generator)",
                 "elements_per_gpu": n, "bytes_per_gpu": nbytes, "l2": "input (4 GiB) >> 126 MB L2, every step streams from HBM",
                 "parallelism": f"shard{world}" if distributed else "single",
-                "collective": "nccl all_gather of 64-byte records + combine kernel" if distributed else None,
+                "collective": (None if not distributed else
+                               "fused in-kernel peer exchange of 64-byte records over NVLink (CUDA IPC), no NCCL on the step"
+                               if sharded.exchange == "peer" else
+                               "nccl all_gather of 64-byte records + combine kernel"),
                 "tuning": tuning, "grid": ll["grid"], "block": ll["threads"],
             },
             "elements_per_s": round(world * n / (ms_per_step / 1e3), 1),

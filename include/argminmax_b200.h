@@ -64,7 +64,8 @@ typedef enum amm_status {
   AMM_ERR_ALIGN = 3,    /* device pointer not aligned to sizeof(element)            */
   AMM_ERR_CUDA = 4,     /* a CUDA call failed (amm_last_cuda_error() has the code)  */
   AMM_ERR_NCCL = 5,     /* NCCL unavailable or a collective failed                  */
-  AMM_ERR_TOO_LARGE = 6 /* more than 2^32-2 scan tiles (>= 32 TiB of input)         */
+  AMM_ERR_TOO_LARGE = 6, /* more than 2^32-2 scan tiles (>= 32 TiB of input)        */
+  AMM_ERR_PEER = 7       /* fused peer exchange: a rank never delivered its record  */
 } amm_status;
 
 /*
@@ -171,6 +172,30 @@ int amm_combine_records(const amm_record* records, int count, int mode, uint64_t
 int amm_combine_records_launch(const void* dev_records, int count, int mode, amm_workspace* ws,
                                void* stream);
 
+/* ------------------------------- fused scan + cross-GPU exchange (one rank per GPU) */
+/*
+ * One kernel per rank does the scan AND the collective: its last CTA stores the rank's
+ * 64-byte record into every peer's exchange buffer over NVLink (peer-mapped memory), waits
+ * until all `world` records of the call have landed in its own buffer, folds them (ascending
+ * rank order, strict compares) and publishes the GLOBAL record; amm_workspace_wait() then
+ * returns the global (argmin, argmax) on every rank.  No NCCL call and no second launch sits
+ * on the per-call path.  Setup, once per workspace:
+ *   amm_exchange_create   allocates this rank's buffer; `ipc_handle_out` (64 bytes, may be
+ *                         NULL in a single process) receives its cudaIpcMemHandle_t;
+ *   amm_exchange_connect_ipc   other processes: all ranks' handles (world x 64 B, rank order),
+ *                         e.g. gathered once with torch.distributed / MPI;
+ *   amm_exchange_connect_ptrs  same process: the peers' buffer pointers (peer access enabled).
+ * Every rank must issue the same sequence of amm_argminmax_launch_exchange calls (it is a
+ * collective); a shard may be empty (n == 0).  A rank that never arrives makes the others
+ * fail with AMM_ERR_PEER after ~4 s instead of hanging.  Each rank needs its own GPU.
+ */
+int amm_exchange_create(amm_workspace* ws, int world, int rank, void* ipc_handle_out);
+int amm_exchange_connect_ipc(amm_workspace* ws, const void* ipc_handles);
+int amm_exchange_connect_ptrs(amm_workspace* ws, void* const* peer_buffers);
+int amm_exchange_local_buffer(amm_workspace* ws, void** dev_ptr);
+int amm_argminmax_launch_exchange(int dtype, const void* dev_ptr, uint64_t n, int mode,
+                                  uint64_t global_offset, amm_workspace* ws, void* stream);
+
 /* -------------------------------------------------- host slices (step before) */
 /*
  * `&[T]` / Vec<T> in HOST memory (src/lib.rs:679-712): chunked, double-buffered
@@ -200,6 +225,9 @@ int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptr
 /* 1 if the records travel through NCCL, 0 if NCCL could not be loaded and the
    records are read from each device's pinned host record instead */
 int amm_sharded_uses_nccl(const amm_sharded* sh);
+/* 1 if the fused in-kernel peer exchange (amm_exchange_*) is used instead: chosen when all
+   devices are distinct and mutually P2P-capable; AMM_SHARDED_EXCHANGE=nccl|host overrides */
+int amm_sharded_uses_peer_exchange(const amm_sharded* sh);
 /* the per-device workspace of shard g (e.g. to apply amm_workspace_set_tuning) */
 int amm_sharded_workspace(amm_sharded* sh, int g, amm_workspace** ws);
 

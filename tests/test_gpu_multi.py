@@ -75,10 +75,12 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-def test_sharded_nccl_in_process():
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_sharded_multi_gpu_in_process(exchange, monkeypatch):
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs")
     from argminmax_b200 import ShardedDeviceSlice
+    monkeypatch.setenv("AMM_SHARDED_EXCHANGE", exchange)
     g = min(_ngpu(), 8)
     rng = np.random.default_rng(41)
     n = 8_000_003
@@ -86,8 +88,8 @@ def test_sharded_nccl_in_process():
     cuts = [n * (i + 1) // g for i in range(g - 1)]
     shards, _keep = _shards_on(a, cuts, list(range(g)))
     sh = ShardedDeviceSlice(shards)
-    assert sh.uses_nccl
-    for _ in range(3):
+    assert sh.uses_peer_exchange if exchange == "peer" else sh.uses_nccl
+    for _ in range(5):
         assert sh.argminmax() == oracle.argminmax(a, 0)
     a[[n - 1, cuts[0] + 5]] = np.nan
     shards, _keep2 = _shards_on(a, cuts, list(range(g)))
@@ -96,6 +98,13 @@ def test_sharded_nccl_in_process():
     assert sh2.argminmax() == oracle.argminmax(a, 0)
     sh.close()
     sh2.close()
+    # an empty shard in the middle still takes part in the exchange
+    b = random_array("i16", 1_000_000, rng)
+    cuts2 = [400_000] + [400_000] * (g - 2) if g > 2 else [1_000_000]
+    shards, _keep3 = _shards_on(b, cuts2, list(range(g)))
+    sh3 = ShardedDeviceSlice(shards)
+    assert sh3.argminmax() == oracle.argminmax(b, 0)
+    sh3.close()
 
 
 _RANK_SCRIPT = r"""
@@ -118,17 +127,20 @@ for mode, b in ((0, a), (1, None)):
     lo, hi = amm.shard_bounds(n, world, rank, align_elems=8)
     t = torch.from_numpy(b[lo:hi].copy()).cuda()
     ds = amm.DistributedShardedSlice(amm.DeviceSlice.from_torch(t))
+    assert ds.exchange == os.environ["AMM_SHARDED_EXCHANGE"], ds.exchange
     got = ds.nanargminmax() if mode else ds.argminmax()
     exp = oracle.argminmax(b, mode)
     assert got == exp, (rank, mode, got, exp)
-    assert ds.argminmax() == oracle.argminmax(b, 0)
+    for _ in range(4):   # back-to-back collective calls (parity banks of the exchange buffer)
+        assert ds.argminmax() == oracle.argminmax(b, 0)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
 
 
-def test_distributed_one_rank_per_gpu(tmp_path):
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_distributed_one_rank_per_gpu(tmp_path, exchange):
     if _ngpu() < 2:
         pytest.skip("needs >= 2 GPUs")
     g = min(_ngpu(), 8)
@@ -136,5 +148,6 @@ def test_distributed_one_rank_per_gpu(tmp_path):
     script.write_text(_RANK_SCRIPT.format(root=ROOT))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={g}",
            "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)]
-    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, AMM_SHARDED_EXCHANGE=exchange)
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
