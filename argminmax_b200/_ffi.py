@@ -104,8 +104,8 @@ def lib():
     """Load libargminmax_b200.so (building it first if nvcc is here and it is stale)."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
-        if not _build.is_current():
+        path = os.environ.get("AMM_LIB_PATH") or _build.LIB_PATH  # override: A/B experiments only
+        if path == _build.LIB_PATH and not _build.is_current():
             try:
                 _build.build()
             except Exception as e:  # noqa: BLE001 - re-raised below if nothing usable exists

@@ -354,12 +354,11 @@ __device__ __forceinline__ amm_record make_record(const ScanParams& p, const Bes
 // merge rule src/simd/generic.rs:513-520) and publishes the GLOBAL record.  Two parity banks
 // make back-to-back calls safe: a rank can only reach call s+2 after every peer has finished
 // reading call s.  A peer that never arrives trips a ~4 s timeout and is reported in flags.
+// XCHG is a compile-time flag of the kernels: single-GPU launches use instantiations that do
+// not contain this code at all (its mere presence costs the streaming loop ~3 % -- registers,
+// loss of uniform-datapath loop control), multi-GPU launches use the fused instantiations.
 template <typename Key>
-__device__ __forceinline__ void finalize(const ScanParams& p, const Best<Key>& x) {
-  if (p.world <= 1) {
-    if (threadIdx.x == 0) publish_record(p, make_record(p, x));
-    return;
-  }
+__device__ __forceinline__ void exchange_and_publish(const ScanParams& p, const Best<Key>& x) {
   __shared__ amm_record s_mine;
   __shared__ amm_record s_all[XCHG_MAX_WORLD];
   __shared__ uint32_t s_timeout;
@@ -445,6 +444,15 @@ __device__ __forceinline__ void finalize(const ScanParams& p, const Best<Key>& x
   }
 }
 
+template <bool XCHG, typename Key>
+__device__ __forceinline__ void finalize(const ScanParams& p, const Best<Key>& x) {
+  if (XCHG) {
+    exchange_and_publish(p, x);
+  } else {
+    if (threadIdx.x == 0) publish_record(p, make_record(p, x));
+  }
+}
+
 // Cross-CTA reduce: every CTA deposits its Best, the last one to arrive (ticket) folds them.
 // Returns true in the last CTA only, with `b` = grid-wide result.  gridDim.x == 1 skips the
 // round trip through global memory.
@@ -484,7 +492,7 @@ __device__ __forceinline__ bool grid_reduce(const ScanParams& p, Best<Key>& b, B
 // takes a contiguous slice, CTA reduce, ticket, the last CTA folds the partials and
 // publishes.  The dependent chain is load -> reduce -> ticket -> fold -> publish.
 // ---------------------------------------------------------------------------------------
-template <class P>
+template <class P, bool XCHG>
 __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const ScanParams p) {
   using Key = typename P::Key;
   constexpr int VEC = 16, NW = 4, UN = 4;
@@ -535,15 +543,14 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
   if (blockIdx.x == gridDim.x - 1) exact_range<P, false>(p.base, p.tail_start, p.n, x);
   x = block_reduce(x, smem);
   if (!grid_reduce(p, x, smem, &s_is_last)) return;
-  finalize(p, x);
+  finalize<XCHG>(p, x);
 }
 
-template <class P, int VEC, int U, bool PREFETCH, int HINT>
+template <class P, int VEC, int U, bool PREFETCH, int HINT, bool XCHG>
 __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanParams p) {
   using VL = VecLoad<VEC, HINT>;
   using Key = typename P::Key;
   constexpr int NW = VL::NW;
-  constexpr uint32_t VEC_ELEMS = VEC / sizeof(typename P::Elem);
   __shared__ Best<Key> smem[32];
   __shared__ uint32_t s_is_last;
 
@@ -646,7 +653,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   }
   x = block_reduce(x, smem);
 
-  finalize(p, x);
+  finalize<XCHG>(p, x);
 }
 
 }  // namespace amm

@@ -13,30 +13,27 @@ struct VariantDesc {
   const char* name;
 };
 static const VariantDesc kVariants[] __attribute__((unused)) = {
-    {16, 4, 1, 2, "v16x4_pf"},       // 0: 128-bit loads, 64 B/thread/tile, 2 tiles in flight
-    {32, 2, 1, 2, "v32x2_pf"},       // 1: 256-bit loads, 64 B/thread/tile, 2 tiles in flight
-    {32, 4, 1, 2, "v32x4_pf"},       // 2: 256-bit loads, 128 B/thread/tile, 2 tiles in flight
-    {16, 8, 0, 2, "v16x8"},          // 3: 128-bit loads, 128 B/thread/tile, no prefetch
-    {32, 4, 0, 2, "v32x4"},          // 4: 256-bit loads, 128 B/thread/tile, no prefetch
-    {16, 2, 1, 2, "v16x2_pf"},       // 5: small tiles
-    {16, 2, 1, 0, "v16x2_pf_nohint"},  // 6: as 5 without the L2 prefetch-size hint
-    {16, 2, 1, 1, "v16x2_pf_l2_128"},  // 7: as 5 with .L2::128B
-    {32, 1, 1, 2, "v32x1_pf"},       // 8: one 256-bit load per thread per tile
-    {16, 4, 1, 0, "v16x4_pf_nohint"},  // 9: as 0 without the hint
+    {16, 4, 1, 2, "v16x4_pf"},  // 0: 128-bit loads, 64 B/thread/tile, 2 tiles in flight (auto, < 512 MiB)
+    {32, 2, 1, 2, "v32x2_pf"},  // 1: 256-bit loads, 64 B/thread/tile, 2 tiles in flight (auto, >= 512 MiB)
+    {32, 4, 1, 2, "v32x4_pf"},  // 2: 256-bit loads, 128 B/thread/tile, 2 tiles in flight
+    {16, 8, 0, 2, "v16x8"},     // 3: 128-bit loads, 128 B/thread/tile, no software prefetch
+    {16, 2, 1, 2, "v16x2_pf"},  // 4: small tiles
+    {16, 4, 1, 0, "v16x4_pf_nohint"},  // 5: as 0 without the .L2::256B prefetch-size hint
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
-template <class P, int VEC, int U, bool PF, int HINT>
+template <class P, int VEC, int U, bool PF, int HINT, bool XCHG>
 static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
                       cudaStream_t stream) {
-  auto kernel = argminmax_scan_kernel<P, VEC, U, PF, HINT>;
+  auto kernel = argminmax_scan_kernel<P, VEC, U, PF, HINT, XCHG>;
   const int threads = ws->eff_threads;
-  int& occ = ws->occupancy[dtype_slot][variant];
-  if (occ == 0 || ws->occupancy_threads[dtype_slot][variant] != threads) {
+  const int vslot = variant + (XCHG ? kNumVariants : 0);  // fused instantiations cache separately
+  int& occ = ws->occupancy[dtype_slot][vslot];
+  if (occ == 0 || ws->occupancy_threads[dtype_slot][vslot] != threads) {
     int o = 0;
     AMM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, threads, 0));
     occ = o < 1 ? 1 : o;
-    ws->occupancy_threads[dtype_slot][variant] = threads;
+    ws->occupancy_threads[dtype_slot][vslot] = threads;
   }
   const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
   const uint64_t tile_vecs = (uint64_t)threads * U;
@@ -82,7 +79,10 @@ static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) 
   const uint64_t cap = (uint64_t)ws->sm_count * (uint64_t)ws->direct_ctas_per_sm;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  argminmax_direct_kernel<P><<<(unsigned)grid, threads, 0, stream>>>(p);
+  if (p.world > 1)
+    argminmax_direct_kernel<P, true><<<(unsigned)grid, threads, 0, stream>>>(p);
+  else
+    argminmax_direct_kernel<P, false><<<(unsigned)grid, threads, 0, stream>>>(p);
   AMM_CUDA(cudaGetLastError());
   ws->last_grid = (int)grid;
   ws->last_threads = threads;
@@ -101,17 +101,19 @@ static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cuda
   ws->eff_variant = ws->variant >= 0 ? ws->variant : (big ? 1 : 0);
   ws->eff_threads = ws->threads > 0 ? ws->threads : 256;
   ws->eff_ctas_per_sm = ws->ctas_per_sm > 0 ? ws->ctas_per_sm : (big ? 8 : 2);
+  if (p.world > 1) {
+    // fused scan + peer exchange: instantiated for the two automatic shapes only
+    if (ws->eff_variant != 0) ws->eff_variant = 1;
+    return ws->eff_variant == 0 ? launch_one<P, 16, 4, true, 2, true>(ws, p, dtype_slot, 0, stream)
+                                : launch_one<P, 32, 2, true, 2, true>(ws, p, dtype_slot, 1, stream);
+  }
   switch (ws->eff_variant) {
-    case 0: return launch_one<P, 16, 4, true, 2>(ws, p, dtype_slot, 0, stream);
-    case 1: return launch_one<P, 32, 2, true, 2>(ws, p, dtype_slot, 1, stream);
-    case 2: return launch_one<P, 32, 4, true, 2>(ws, p, dtype_slot, 2, stream);
-    case 3: return launch_one<P, 16, 8, false, 2>(ws, p, dtype_slot, 3, stream);
-    case 4: return launch_one<P, 32, 4, false, 2>(ws, p, dtype_slot, 4, stream);
-    case 5: return launch_one<P, 16, 2, true, 2>(ws, p, dtype_slot, 5, stream);
-    case 6: return launch_one<P, 16, 2, true, 0>(ws, p, dtype_slot, 6, stream);
-    case 7: return launch_one<P, 16, 2, true, 1>(ws, p, dtype_slot, 7, stream);
-    case 8: return launch_one<P, 32, 1, true, 2>(ws, p, dtype_slot, 8, stream);
-    case 9: return launch_one<P, 16, 4, true, 0>(ws, p, dtype_slot, 9, stream);
+    case 0: return launch_one<P, 16, 4, true, 2, false>(ws, p, dtype_slot, 0, stream);
+    case 1: return launch_one<P, 32, 2, true, 2, false>(ws, p, dtype_slot, 1, stream);
+    case 2: return launch_one<P, 32, 4, true, 2, false>(ws, p, dtype_slot, 2, stream);
+    case 3: return launch_one<P, 16, 8, false, 2, false>(ws, p, dtype_slot, 3, stream);
+    case 4: return launch_one<P, 16, 2, true, 2, false>(ws, p, dtype_slot, 4, stream);
+    case 5: return launch_one<P, 16, 4, true, 0, false>(ws, p, dtype_slot, 5, stream);
     default: return AMM_ERR_ARG;
   }
 }
