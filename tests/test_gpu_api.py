@@ -1,0 +1,145 @@
+"""C-ABI surface details on the GPU: typed symbols, single-output entry points, stream
+ordering, independent workspaces, error statuses, fuzzed special values."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import golden_util as G
+from tests.gpu_util import assert_parity, modes_for, random_array, to_device
+
+pytestmark = pytest.mark.gpu
+
+
+def test_typed_symbols_and_single_output_entry_points():
+    """amm_argminmax_<dt> (one per `impl ArgMinMax for &[T]`, src/lib.rs:657-664) and
+    amm_argmin / amm_argmax (src/lib.rs:170,185,227,243) agree with the generic entry point."""
+    from argminmax_b200 import DTYPES, default_workspace, lib
+    L = lib()
+    rng = np.random.default_rng(55)
+    ws = default_workspace(0)
+    for dt in G.ALL_DTYPES:
+        a = random_array(dt, 70_001, rng)
+        if dt in G.FLOAT_DTYPES:
+            a[[5000, 60_000]] = np.nan
+        ds, _keep = to_device(a)
+        for mode in modes_for(dt):
+            exp = oracle.argminmax(a, mode)
+            out = (ctypes.c_uint64 * 2)()
+            rc = getattr(L, f"amm_argminmax_{dt}")(ds.data_ptr, ds.n, mode, ws.handle, None, out)
+            assert rc == 0 and (out[0], out[1]) == exp
+            one = (ctypes.c_uint64 * 1)()
+            assert L.amm_argmin(DTYPES[dt], ds.data_ptr, ds.n, mode, ws.handle, None, one) == 0
+            assert one[0] == exp[0]
+            assert L.amm_argmax(DTYPES[dt], ds.data_ptr, ds.n, mode, ws.handle, None, one) == 0
+            assert one[0] == exp[1]
+
+
+def test_error_statuses():
+    from argminmax_b200 import _ffi, default_workspace, lib
+    import torch
+    L = lib()
+    ws = default_workspace(0)
+    t = torch.zeros(64, dtype=torch.float32, device="cuda:0")
+    out = (ctypes.c_uint64 * 2)()
+    assert L.amm_argminmax(9, t.data_ptr(), 0, 0, ws.handle, None, out) == _ffi.AMM_ERR_EMPTY
+    assert L.amm_argminmax(99, t.data_ptr(), 4, 0, ws.handle, None, out) == _ffi.AMM_ERR_ARG
+    assert L.amm_argminmax(9, t.data_ptr(), 4, 7, ws.handle, None, out) == _ffi.AMM_ERR_ARG
+    assert L.amm_argminmax(9, None, 4, 0, ws.handle, None, out) == _ffi.AMM_ERR_ARG
+    assert L.amm_argminmax(9, t.data_ptr() + 2, 4, 0, ws.handle, None, out) == _ffi.AMM_ERR_ALIGN
+    assert L.amm_argminmax(9, t.data_ptr(), 4, 0, None, None, out) == _ffi.AMM_ERR_ARG
+    h = ctypes.c_void_p()
+    assert L.amm_workspace_create(1000, ctypes.byref(h)) == _ffi.AMM_ERR_ARG
+
+
+def test_stream_ordering_without_host_sync():
+    """The scan is enqueued on the caller's stream: data written by an earlier kernel on that
+    stream is seen without any host synchronisation in between."""
+    import torch
+
+    from argminmax_b200 import DeviceSlice, Workspace
+    s = torch.cuda.Stream()
+    ws = Workspace(0)
+    n = 50_000_000
+    with torch.cuda.stream(s):
+        t = torch.zeros(n, dtype=torch.float32, device="cuda:0")
+        for k in range(5):
+            t.fill_(1.0)
+            t[1234 + k] = -5.0
+            t[n - 77 - k] = 9.0
+            ds = DeviceSlice.from_torch(t, workspace=ws, stream=s.cuda_stream)
+            assert ds.argminmax() == (1234 + k, n - 77 - k)
+    ws.close()
+
+
+def test_independent_workspaces_on_two_streams():
+    import torch
+
+    from argminmax_b200 import DeviceSlice, Workspace
+    rng = np.random.default_rng(77)
+    a = random_array("f32", 30_000_001, rng)
+    b = random_array("i16", 60_000_003, rng)
+    da, _ka = to_device(a)
+    db, _kb = to_device(b)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    w1, w2 = Workspace(0), Workspace(0)
+    da._ws, da.stream = w1, s1.cuda_stream
+    db._ws, db.stream = w2, s2.cuda_stream
+    ea, eb = oracle.argminmax(a, 0), oracle.argminmax(b, 0)
+    for _ in range(10):
+        da.launch(0)
+        db.launch(0)
+        da.launch(0)
+        db.launch(0)
+        assert db.wait(0) == eb
+        assert da.wait(0) == ea
+    w1.close()
+    w2.close()
+
+
+SPECIALS = {
+    "f16": [np.float16(x) for x in (np.nan, np.inf, -np.inf, 0.0, -0.0, 65504, -65504, 6e-8, -6e-8, 1, -1)],
+    "f32": [np.float32(x) for x in (np.nan, np.inf, -np.inf, 0.0, -0.0, 3.4028235e38, -3.4028235e38,
+                                    1e-45, -1e-45, 1, -1)],
+    "f64": [np.float64(x) for x in (np.nan, np.inf, -np.inf, 0.0, -0.0, 1.7976931348623157e308,
+                                    -1.7976931348623157e308, 5e-324, -5e-324, 1, -1)],
+}
+
+
+# non-canonical NaNs: negative, signalling, all-ones payload (SURVEY A.3 #3/#4 policy: the CUDA
+# path treats every NaN bit pattern like the reference's SCALAR code does)
+SPECIALS["f16"] += list(np.array([0xFE00, 0x7C01, 0xFFFF, 0xFC01], dtype=np.uint16).view(np.float16))
+SPECIALS["f32"] += list(np.array([0xFFC00000, 0x7F800001, 0xFFFFFFFF, 0xFF800001], dtype=np.uint32).view(np.float32))
+SPECIALS["f64"] += list(np.array([0xFFF8000000000000, 0x7FF0000000000001, 0xFFFFFFFFFFFFFFFF,
+                                  0xFFF0000000000001], dtype=np.uint64).view(np.float64))
+
+
+@pytest.mark.parametrize("dt", G.ALL_DTYPES)
+def test_fuzz_special_values_sizes_alignments(dt):
+    """Seeded fuzz: random length, random base alignment, a random sprinkling of special values
+    (NaN, +-inf, +-0, type min/max, subnormals; ints: type min/max/0) with many duplicates."""
+    rng = np.random.default_rng(1000 + G.ALL_DTYPES.index(dt))
+    T = G.NP[dt]
+    es = np.dtype(T).itemsize
+    for _case in range(60):
+        n = int(rng.integers(1, 300_000)) if rng.random() < 0.7 else int(rng.integers(1, 200))
+        if rng.random() < 0.5:
+            a = random_array(dt, n, rng)
+        else:  # small value range => lots of ties
+            a = rng.integers(0, 4, n).astype(T)
+        if dt in G.FLOAT_DTYPES:
+            specials = SPECIALS[dt]
+        else:
+            info = np.iinfo(T)
+            specials = [T(info.min), T(info.max), T(0)]
+        k = int(rng.integers(0, max(2, n // 50)))
+        if k:
+            pos = rng.integers(0, n, k)
+            sp = np.array(specials, dtype=T)
+            # assign through the raw bits so that NaN payloads survive
+            U = {1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[es]
+            a.view(U)[pos] = sp.view(U)[rng.integers(0, len(sp), k)]
+        off = int(rng.integers(0, 64 // es)) * es
+        for mode in modes_for(dt):
+            assert_parity(a, mode, byte_offset=off, what="fuzz")
