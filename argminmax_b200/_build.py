@@ -58,30 +58,51 @@ def _compile(nvcc: str, src: str, obj: str, extra: list[str], verbose: bool) -> 
     return proc.stderr
 
 
+DEBUG_LIB_PATH = os.path.join(LIB_DIR, "libargminmax_b200_boundscheck.so")
+DEBUG_STAMP = os.path.join(LIB_DIR, "build_boundscheck.stamp")
+
+
+def _build_into(lib_path: str, stamp: str, obj_dir: str, defines: list[str], verbose: bool) -> str:
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    jobs = [(src, os.path.join(obj_dir, src.replace(".cu", ".o")), list(defines))
+            for src in SOURCES if src != "scan_inst.cu"]
+    jobs += [("scan_inst.cu", os.path.join(obj_dir, f"scan_inst_g{k}.o"),
+              [f"-DAMM_GROUP={k}", *defines]) for k in range(N_GROUPS)]
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        logs = list(ex.map(lambda j: _compile(nvcc, j[0], j[1], j[2], verbose), jobs))
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path,
+            *[j[1] for j in jobs], "-ldl"]
+    proc = subprocess.run(link, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("link failed:\n" + proc.stdout + proc.stderr)
+    with open(stamp, "w") as f:
+        f.write(_fingerprint())
+    if verbose:
+        print("\n".join(logs))
+    return lib_path
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the library if the sources changed since the last build. Returns its path.
     Every translation unit is built with -gencode arch=compute_100a,code=sm_100a -lineinfo."""
     if not force and is_current():
         return LIB_PATH
-    from concurrent.futures import ThreadPoolExecutor
-    os.makedirs(OBJ_DIR, exist_ok=True)
-    nvcc = _nvcc()
-    jobs = [(src, os.path.join(OBJ_DIR, src.replace(".cu", ".o")), [])
-            for src in SOURCES if src != "scan_inst.cu"]
-    jobs += [("scan_inst.cu", os.path.join(OBJ_DIR, f"scan_inst_g{k}.o"), [f"-DAMM_GROUP={k}"])
-             for k in range(N_GROUPS)]
-    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
-        logs = list(ex.map(lambda j: _compile(nvcc, j[0], j[1], j[2], verbose), jobs))
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH,
-            *[j[1] for j in jobs], "-ldl"]
-    proc = subprocess.run(link, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("link failed:\n" + proc.stdout + proc.stderr)
-    with open(STAMP, "w") as f:
-        f.write(_fingerprint())
-    if verbose:
-        print("\n".join(logs))
-    return LIB_PATH
+    return _build_into(LIB_PATH, STAMP, OBJ_DIR, [], verbose)
+
+
+def build_boundscheck(force: bool = False) -> str:
+    """Debug twin of the library (-DAMM_BOUNDS_CHECK): every global load of input data is
+    checked against [base, base + n*sizeof(T)); a violation makes the call fail.  Used by
+    tests/test_gpu_bounds.py in place of compute-sanitizer (closed on this pool)."""
+    if not force and os.path.exists(DEBUG_LIB_PATH) and os.path.exists(DEBUG_STAMP):
+        with open(DEBUG_STAMP) as f:
+            if f.read().strip() == _fingerprint():
+                return DEBUG_LIB_PATH
+    return _build_into(DEBUG_LIB_PATH, DEBUG_STAMP, OBJ_DIR + "_boundscheck",
+                       ["-DAMM_BOUNDS_CHECK"], False)
 
 
 if __name__ == "__main__":

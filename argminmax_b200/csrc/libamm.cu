@@ -106,6 +106,14 @@ int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global
   memset(&p, 0, sizeof(p));
   p.base = (const uint8_t*)dev_ptr;
   p.n = n;
+  p.n_bytes = n * es;
+#ifdef AMM_BOUNDS_CHECK
+  // self-test of the checker: pretend the array is shorter than what the kernels will scan
+  if (getenv("AMM_DEBUG_SHRINK_BYTES")) {
+    const uint64_t k = strtoull(getenv("AMM_DEBUG_SHRINK_BYTES"), nullptr, 10);
+    p.n_bytes = p.n_bytes > k ? p.n_bytes - k : 0;
+  }
+#endif
   p.global_offset = global_offset;
   p.partials = ws->partials;
   p.ticket = ws->ticket;
@@ -223,6 +231,8 @@ using namespace amm;
 
 extern "C" {
 
+int amm_workspace_destroy(amm_workspace* ws);
+
 int amm_combine_records_launch(const void* dev_records, int count, int mode, amm_workspace* ws,
                                void* stream) {
   if (!dev_records || !ws || count < 1) return AMM_ERR_ARG;
@@ -236,16 +246,7 @@ int amm_combine_records_launch(const void* dev_records, int count, int mode, amm
   return AMM_OK;
 }
 
-int amm_workspace_create(int device, amm_workspace** out) {
-  if (out == nullptr) return AMM_ERR_ARG;
-  *out = nullptr;
-  int count = 0;
-  AMM_CUDA(cudaGetDeviceCount(&count));
-  if (device < 0 || device >= count) return AMM_ERR_ARG;
-  int rc = set_device(device);
-  if (rc) return rc;
-  amm_workspace* ws = new (std::nothrow) amm_workspace();
-  if (!ws) return AMM_ERR_ARG;
+static int workspace_init(amm_workspace* ws, int device) {
   memset(ws, 0, sizeof(*ws));
   ws->device = device;
   cudaDeviceProp prop;
@@ -257,9 +258,14 @@ int amm_workspace_create(int device, amm_workspace** out) {
   ws->direct_bytes = (uint64_t)8 << 20;
   ws->direct_threads = 256;
   ws->direct_ctas_per_sm = 2;
+  // experiment knobs (tools/, profiling); the defaults are the tuned values
   if (getenv("AMM_DIRECT_BYTES")) ws->direct_bytes = strtoull(getenv("AMM_DIRECT_BYTES"), nullptr, 10);
   if (getenv("AMM_DIRECT_THREADS")) ws->direct_threads = atoi(getenv("AMM_DIRECT_THREADS"));
   if (getenv("AMM_DIRECT_CTAS")) ws->direct_ctas_per_sm = atoi(getenv("AMM_DIRECT_CTAS"));
+  if (ws->direct_threads < 64 || ws->direct_threads > MAX_THREADS || ws->direct_threads % 32)
+    ws->direct_threads = 256;
+  if (ws->direct_ctas_per_sm < 1 || ws->direct_ctas_per_sm > 32) ws->direct_ctas_per_sm = 2;
+  ws->publish_fence = getenv("AMM_PUBLISH_FENCE") ? atoi(getenv("AMM_PUBLISH_FENCE")) : 0;
   ws->max_grid = ws->sm_count * 32;
   // partials sized for the widest Best<int64_t> (40 B) -> 64 B slots
   AMM_CUDA(cudaMalloc(&ws->partials, (size_t)ws->max_grid * 64));
@@ -269,9 +275,28 @@ int amm_workspace_create(int device, amm_workspace** out) {
   AMM_CUDA(cudaMemset(ws->rec_dev, 0, sizeof(amm_record)));
   AMM_CUDA(cudaHostAlloc((void**)&ws->rec_host, 128, cudaHostAllocMapped));
   memset(ws->rec_host, 0, 128);
-  ws->publish_fence = getenv("AMM_PUBLISH_FENCE") ? atoi(getenv("AMM_PUBLISH_FENCE")) : 0;
   AMM_CUDA(cudaHostGetDevicePointer((void**)&ws->rec_host_dev, ws->rec_host, 0));
   AMM_CUDA(cudaDeviceSynchronize());
+  return AMM_OK;
+}
+
+int amm_workspace_create(int device, amm_workspace** out) {
+  if (out == nullptr) return AMM_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  AMM_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return AMM_ERR_ARG;
+  int rc = set_device(device);
+  if (rc) return rc;
+  amm_workspace* ws = new (std::nothrow) amm_workspace();
+  if (!ws) return AMM_ERR_ARG;
+  rc = workspace_init(ws, device);
+  if (rc) {  // release whatever was allocated before the failure
+    const int saved = g_last_cuda_error;
+    amm_workspace_destroy(ws);
+    g_last_cuda_error = saved;
+    return rc;
+  }
   *out = ws;
   return AMM_OK;
 }
@@ -367,6 +392,8 @@ int amm_argminmax_launch_exchange(int dtype, const void* dev_ptr, uint64_t n, in
 
 int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2]) {
   if (!ws || !out) return AMM_ERR_ARG;
+  if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
+  if (ws->seq == 0) return AMM_ERR_ARG;  // nothing was ever launched on this workspace
   // The kernel publishes the record into pinned host memory and writes `seq` last (after a
   // system-scope fence), so the host can pick the answer up by polling that word -- a few
   // microseconds sooner than cudaStreamSynchronize returns.  The stream is queried now and
@@ -392,6 +419,7 @@ int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2
     if (!read_host_slot(ws, want, &r)) return AMM_ERR_CUDA;  // record never published
   }
   if (r.flags & AMM_REC_PEER_TIMEOUT) return AMM_ERR_PEER;
+  if (r.flags & AMM_REC_BOUNDS) return AMM_ERR_CUDA;  // debug builds: a load left the input range
   combine(&r, 1, mode, out);
   return AMM_OK;
 }

@@ -45,6 +45,7 @@ constexpr int MAX_THREADS = 512;
 struct ScanParams {
   const uint8_t* base;     // caller's device pointer (element 0)
   uint64_t n;              // elements
+  uint64_t n_bytes;        // n * sizeof(element)
   uint64_t global_offset;  // added to every reported index (shard offset)
   uint64_t head_elems;     // elements before the first VEC-aligned address (<= n)
   uint64_t n_vec;          // whole vectors in the aligned main region
@@ -64,6 +65,27 @@ struct ScanParams {
   uint64_t* const* peer_slots;  // device array [world]: every rank's exchange buffer, peer-mapped
   uint64_t xseq;               // exchange sequence number, identical on all ranks
 };
+
+// Debug builds (-DAMM_BOUNDS_CHECK, tools/build_debug.py) verify that every global load of input
+// data lies inside [base, base + n_bytes); violations are counted in a scratch word and
+// surface as AMM_REC_BOUNDS in the record (compute-sanitizer is not available on the pool).
+struct Bounds {
+#ifdef AMM_BOUNDS_CHECK
+  const uint8_t* lo;
+  const uint8_t* hi;
+  uint32_t* err;
+  __device__ __forceinline__ explicit Bounds(const ScanParams& p)
+      : lo(p.base), hi(p.base + p.n_bytes), err(p.ticket + 8) {}
+  __device__ __forceinline__ void check(const void* ptr, uint32_t bytes) const {
+    const uint8_t* a = static_cast<const uint8_t*>(ptr);
+    if (a < lo || a + bytes > hi) atomicAdd(err, 1u);
+  }
+#else
+  __device__ __forceinline__ explicit Bounds(const ScanParams&) {}
+  __device__ __forceinline__ void check(const void*, uint32_t) const {}
+#endif
+};
+constexpr uint64_t AMM_REC_BOUNDS = 8ull;  // record.flags bit (debug builds only)
 
 constexpr int XCHG_SLOT_WORDS = 16;     // 128 B per (parity, rank) slot: 8 record words,
 constexpr int XCHG_MAX_WORLD = 16;      // checksum, tag; 2 parities per buffer
@@ -214,8 +236,8 @@ __device__ __forceinline__ void fold_tile(const uint32_t (&v)[U][NW], uint32_t t
 // index >= begin, so a strict compare keeps the first occurrence; otherwise ranges may come
 // in any order and the full lexicographic rule is applied.
 template <class P, bool ASCENDING>
-__device__ __forceinline__ void exact_range(const uint8_t* base, uint64_t begin, uint64_t end,
-                                            Best<typename P::Key>& b) {
+__device__ __forceinline__ void exact_range(const Bounds& bd, const uint8_t* base, uint64_t begin,
+                                            uint64_t end, Best<typename P::Key>& b) {
   using Elem = typename P::Elem;
   using Key = typename P::Key;
   const Elem* e = reinterpret_cast<const Elem*>(base);
@@ -225,6 +247,7 @@ __device__ __forceinline__ void exact_range(const uint8_t* base, uint64_t begin,
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const uint64_t i = i0 + (uint64_t)u * blockDim.x;
+      if (i < end) bd.check(&e[i], sizeof(Elem));
       raw[u] = (i < end) ? e[i] : Elem(0);
     }
 #pragma unroll
@@ -269,8 +292,8 @@ __device__ __forceinline__ typename P::Elem vec_elem(const uint32_t (&w)[NW], in
 // same vector loads and thread->vector mapping as the streaming phase: one round trip to
 // memory for the whole tile.
 template <class P, int VEC, int U>
-__device__ __forceinline__ void exact_tile(const uint8_t* main_base, uint64_t head_elems,
-                                           uint64_t tile0, uint64_t n_vec,
+__device__ __forceinline__ void exact_tile(const Bounds& bd, const uint8_t* main_base,
+                                           uint64_t head_elems, uint64_t tile0, uint64_t n_vec,
                                            Best<typename P::Key>& b) {
   using Key = typename P::Key;
   constexpr int NW = VecLoad<VEC>::NW;
@@ -280,7 +303,10 @@ __device__ __forceinline__ void exact_tile(const uint8_t* main_base, uint64_t he
 #pragma unroll
   for (int j = 0; j < U; ++j) {
     const uint64_t vi = v0 + (uint64_t)j * blockDim.x;
-    if (vi < n_vec) VecLoad<VEC>::ld(main_base + vi * VEC, w[j]);
+    if (vi < n_vec) {
+      bd.check(main_base + vi * VEC, VEC);
+      VecLoad<VEC>::ld(main_base + vi * VEC, w[j]);
+    }
   }
 #pragma unroll
   for (int j = 0; j < U; ++j) {
@@ -340,6 +366,9 @@ __device__ __forceinline__ amm_record make_record(const ScanParams& p, const Bes
   r.max_idx = has_value ? x.pmax + p.global_offset : AMM_NO_INDEX;
   r.nan_idx = has_nan ? x.pnan + p.global_offset : AMM_NO_INDEX;
   r.flags = (has_value ? AMM_REC_HAS_VALUE : 0ull) | (has_nan ? AMM_REC_HAS_NAN : 0ull);
+#ifdef AMM_BOUNDS_CHECK
+  if (atomicExch(p.ticket + 8, 0u) != 0u) r.flags |= AMM_REC_BOUNDS;
+#endif
   r.n = p.n;
   r.seq = p.seq;
   return r;
@@ -500,6 +529,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
   __shared__ Best<Key> smem[32];
   __shared__ uint32_t s_is_last;
   const uint8_t* main_base = p.base + p.head_elems * sizeof(typename P::Elem);
+  const Bounds bd(p);
   // contiguous slice of whole vectors per CTA, coalesced 128-bit loads, UN in flight
   const uint64_t per = (p.n_vec + gridDim.x - 1) / gridDim.x;
   const uint64_t vb = per * blockIdx.x;
@@ -512,7 +542,10 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
-      if (vi < ve) VecLoad<VEC>::ld(main_base + vi * VEC, w[u]);
+      if (vi < ve) {
+        bd.check(main_base + vi * VEC, VEC);
+        VecLoad<VEC>::ld(main_base + vi * VEC, w[u]);
+      }
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -539,8 +572,8 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
     }
   }
   // unaligned head / sub-vector tail (< 16 B each): lexicographic merges, any order
-  if (blockIdx.x == 0) exact_range<P, false>(p.base, 0, p.head_elems, x);
-  if (blockIdx.x == gridDim.x - 1) exact_range<P, false>(p.base, p.tail_start, p.n, x);
+  if (blockIdx.x == 0) exact_range<P, false>(bd, p.base, 0, p.head_elems, x);
+  if (blockIdx.x == gridDim.x - 1) exact_range<P, false>(bd, p.base, p.tail_start, p.n, x);
   x = block_reduce(x, smem);
   if (!grid_reduce(p, x, smem, &s_is_last)) return;
   finalize<XCHG>(p, x);
@@ -557,6 +590,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   const uint32_t tile_vecs = blockDim.x * U;
   const uint64_t tile_bytes = (uint64_t)tile_vecs * VEC;
   const uint8_t* main_base = p.base + p.head_elems * sizeof(typename P::Elem);
+  const Bounds bd(p);
 
   Running<Key> run;
   run.kmin = KeyLim<Key>::MAXV;
@@ -577,14 +611,20 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
       if (t < nft) {
         const uint8_t* q = lane_base + (uint64_t)t * tile_bytes;
 #pragma unroll
-        for (int j = 0; j < U; ++j) VL::ld(q + j * jstride, a[j]);
+        for (int j = 0; j < U; ++j) {
+          bd.check(q + j * jstride, VEC);
+          VL::ld(q + j * jstride, a[j]);
+        }
       }
       while (t < nft) {
         const uint32_t t1 = t + gridDim.x;
         if (t1 < nft) {
           const uint8_t* q = lane_base + (uint64_t)t1 * tile_bytes;
 #pragma unroll
-          for (int j = 0; j < U; ++j) VL::ld(q + j * jstride, b[j]);
+          for (int j = 0; j < U; ++j) {
+            bd.check(q + j * jstride, VEC);
+            VL::ld(q + j * jstride, b[j]);
+          }
         }
         fold_tile<P, NW, U>(a, t + 1, run);
         if (t1 >= nft) break;
@@ -592,7 +632,10 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
         if (t2 < nft) {
           const uint8_t* q = lane_base + (uint64_t)t2 * tile_bytes;
 #pragma unroll
-          for (int j = 0; j < U; ++j) VL::ld(q + j * jstride, a[j]);
+          for (int j = 0; j < U; ++j) {
+          bd.check(q + j * jstride, VEC);
+          VL::ld(q + j * jstride, a[j]);
+        }
         }
         fold_tile<P, NW, U>(b, t1 + 1, run);
         t = t2;
@@ -601,7 +644,10 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
       for (; t < nft; t += gridDim.x) {
         const uint8_t* q = lane_base + (uint64_t)t * tile_bytes;
 #pragma unroll
-        for (int j = 0; j < U; ++j) VL::ld(q + j * jstride, a[j]);
+        for (int j = 0; j < U; ++j) {
+          bd.check(q + j * jstride, VEC);
+          VL::ld(q + j * jstride, a[j]);
+        }
         fold_tile<P, NW, U>(a, t + 1, run);
       }
     }
@@ -611,10 +657,12 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
     uint32_t cur[U][NW];
     const uint8_t* q =
         main_base + (uint64_t)p.n_full_tiles * tile_bytes + (uint64_t)threadIdx.x * VEC;
+    bd.check(q, VEC);
     VL::ld(q, cur[0]);
 #pragma unroll
     for (int j = 1; j < U; ++j) {
       if ((uint32_t)j * blockDim.x + threadIdx.x < p.rem_vecs) {
+        bd.check(q + (uint64_t)j * blockDim.x * VEC, VEC);
         VL::ld(q + (uint64_t)j * blockDim.x * VEC, cur[j]);
       } else {  // duplicates are neutral for a value-only min/max
 #pragma unroll
@@ -640,8 +688,8 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   // ------------------- exact (key, index) scan of the few candidate ranges
   Best<Key> x;
   x.clear();
-  exact_range<P, false>(p.base, 0, p.head_elems, x);
-  exact_range<P, false>(p.base, p.tail_start, p.n, x);
+  exact_range<P, false>(bd, p.base, 0, p.head_elems, x);
+  exact_range<P, false>(bd, p.base, p.tail_start, p.n, x);
   const uint64_t cand[3] = {g.pmin, g.pmax, g.pnan};
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
@@ -649,7 +697,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
     if (tid == POS_NONE) continue;
     if (c == 1 && tid == cand[0]) continue;
     if (c == 2 && (tid == cand[0] || tid == cand[1])) continue;
-    exact_tile<P, VEC, U>(main_base, p.head_elems, tid - 1, p.n_vec, x);
+    exact_tile<P, VEC, U>(bd, main_base, p.head_elems, tid - 1, p.n_vec, x);
   }
   x = block_reduce(x, smem);
 

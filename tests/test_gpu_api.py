@@ -51,6 +51,11 @@ def test_error_statuses():
     assert L.amm_argminmax(9, t.data_ptr(), 4, 0, None, None, out) == _ffi.AMM_ERR_ARG
     h = ctypes.c_void_p()
     assert L.amm_workspace_create(1000, ctypes.byref(h)) == _ffi.AMM_ERR_ARG
+    # waiting on a workspace that never launched anything is an argument error, not a hang
+    from argminmax_b200 import Workspace
+    fresh = Workspace(0)
+    assert L.amm_workspace_wait(fresh.handle, None, 0, out) == _ffi.AMM_ERR_ARG
+    fresh.close()
 
 
 def test_stream_ordering_without_host_sync():
