@@ -127,6 +127,27 @@ class DeviceSlice:
         return cls(tensor.data_ptr(), nbytes // DTYPE_SIZE[name], name, tensor.device.index or 0,
                    workspace, stream, owner=tensor)
 
+    @classmethod
+    def from_dlpack(cls, obj, dtype: Optional[str] = None, workspace: Optional[Workspace] = None,
+                    stream: int = 0) -> "DeviceSlice":
+        """Any producer of a CUDA DLPack capsule (`__dlpack__`): cupy, jax, numba, torch ..."""
+        import torch
+        return cls.from_torch(torch.from_dlpack(obj), dtype=dtype, workspace=workspace, stream=stream)
+
+    @classmethod
+    def from_cuda_array_interface(cls, obj, workspace: Optional[Workspace] = None,
+                                  stream: int = 0, device: int = 0) -> "DeviceSlice":
+        """Objects exposing `__cuda_array_interface__` (numba / cupy device arrays), no copy."""
+        cai = obj.__cuda_array_interface__
+        shape, typestr = cai["shape"], cai["typestr"]
+        if len(shape) != 1 or cai.get("strides") not in (None, (int(typestr[2:]),)):
+            raise ValueError("DeviceSlice needs a contiguous 1-D array")
+        kinds = {"i": "i", "u": "u", "f": "f"}
+        if typestr[0] not in "<|" or typestr[1] not in kinds:
+            raise TypeError(f"unsupported typestr {typestr}")
+        name = f"{kinds[typestr[1]]}{int(typestr[2:]) * 8}"
+        return cls(cai["data"][0], shape[0], name, device, workspace, stream, owner=obj)
+
     def __len__(self):
         return self.n
 
@@ -201,6 +222,26 @@ class HostSlice:
         if arr.ndim != 1 or not arr.flags["C_CONTIGUOUS"]:
             raise ValueError("HostSlice needs a contiguous 1-D array")
         return cls(arr.ctypes.data, arr.size, from_np[arr.dtype], device, workspace, owner=arr)
+
+    @classmethod
+    def from_arrow(cls, arr, device: int = 0, workspace: Optional[Workspace] = None) -> "HostSlice":
+        """Arrow `PrimitiveArray` -> its values buffer (the reference's arrow adapter,
+        src/lib.rs:764-810: `self.values()`, i.e. the validity bitmap is IGNORED and null
+        slots are scanned with whatever value they hold).  Zero-copy; honours the array offset."""
+        import pyarrow as pa
+        if isinstance(arr, pa.ChunkedArray):
+            if arr.num_chunks != 1:
+                raise ValueError("HostSlice.from_arrow needs a single contiguous chunk")
+            arr = arr.chunk(0)
+        names = {pa.int8(): "i8", pa.int16(): "i16", pa.int32(): "i32", pa.int64(): "i64",
+                 pa.uint8(): "u8", pa.uint16(): "u16", pa.uint32(): "u32", pa.uint64(): "u64",
+                 pa.float16(): "f16", pa.float32(): "f32", pa.float64(): "f64"}
+        if arr.type not in names:
+            raise TypeError(f"unsupported arrow type {arr.type}")
+        name = names[arr.type]
+        values = arr.buffers()[1]
+        ptr = values.address + arr.offset * DTYPE_SIZE[name]
+        return cls(ptr, len(arr), name, device, workspace, owner=(arr, values))
 
     @classmethod
     def from_torch(cls, tensor, dtype: Optional[str] = None, device: int = 0,

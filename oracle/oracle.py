@@ -35,8 +35,10 @@ RETURN_NAN = 1
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so / libcpusimd.so with the committed Makefile (gcc only)."""
-    targets = [os.path.join(_HERE, "liboracle.so"), os.path.join(_HERE, "libcpusimd.so")]
-    srcs = [os.path.join(_HERE, "argminmax_oracle.c"), os.path.join(_HERE, "cpu_simd_f32.c")]
+    targets = [os.path.join(_HERE, "liboracle.so"), os.path.join(_HERE, "libcpusimd.so"),
+               os.path.join(_HERE, "libsimdemul.so")]
+    srcs = [os.path.join(_HERE, "argminmax_oracle.c"), os.path.join(_HERE, "cpu_simd_f32.c"),
+            os.path.join(_HERE, "simd_emul.c")]
     stale = force or any(
         (not os.path.exists(t)) or os.path.getmtime(t) < os.path.getmtime(s)
         for t, s in zip(targets, srcs)
@@ -122,6 +124,28 @@ def argmax(arr: np.ndarray, mode: int = IGNORE_NAN) -> int:
     if rc:
         raise ValueError("empty input" if rc == 1 else f"oracle error {rc}")
     return int(out[0])
+
+
+_emul = None
+
+
+def simd_emul_argminmax(arr: np.ndarray, mode: int = IGNORE_NAN, isa: int = 0) -> tuple[int, int]:
+    """Lane-exact emulation of the reference's DISPATCHED SIMD path (oracle/simd_emul.c):
+    isa 0 = what an AVX-512 host runs, isa 1 = what an AVX2 host runs."""
+    global _emul
+    if _emul is None:
+        build()
+        _emul = ctypes.CDLL(os.path.join(_HERE, "libsimdemul.so"))
+        _emul.simd_emul_argminmax.restype = ctypes.c_int
+        _emul.simd_emul_argminmax.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64,
+                                              ctypes.c_int, ctypes.c_int,
+                                              ctypes.POINTER(ctypes.c_uint64)]
+    arr, code = _prep(arr)
+    out = (ctypes.c_uint64 * 2)()
+    rc = _emul.simd_emul_argminmax(code, arr.ctypes.data, arr.size, mode, isa, out)
+    if rc:
+        raise ValueError("empty input" if rc == 1 else f"simd_emul error {rc}")
+    return int(out[0]), int(out[1])
 
 
 ISA_NAMES = {0: "scalar", 1: "avx", 2: "avx512f"}

@@ -148,3 +148,35 @@ def test_fuzz_special_values_sizes_alignments(dt):
         off = int(rng.integers(0, 64 // es)) * es
         for mode in modes_for(dt):
             assert_parity(a, mode, byte_offset=off, what="fuzz")
+
+
+def test_arrow_and_dlpack_adapters():
+    """Row (f) of SURVEY 8: Arrow values buffer (validity bitmap ignored, like src/lib.rs:777)
+    and DLPack / __cuda_array_interface__ producers, all zero-copy views."""
+    import pyarrow as pa
+    import torch
+
+    from argminmax_b200 import DeviceSlice, HostSlice
+    rng = np.random.default_rng(91)
+    a = random_array("f64", 2_000_003, rng)
+    arr = pa.array(a)
+    assert HostSlice.from_arrow(arr).argminmax() == oracle.argminmax(a, 0)
+    sl = arr.slice(12_345, 1_000_000)       # non-zero offset
+    assert HostSlice.from_arrow(sl).argminmax() == oracle.argminmax(a[12_345:1_012_345], 0)
+    # nulls are ignored exactly like the reference's adapter: the slot's stored value counts
+    b = rng.integers(-1000, 1000, 100_000).astype(np.int32)
+    b[777] = -5000
+    masked = pa.array(b, mask=(np.arange(b.size) == 777))
+    got = HostSlice.from_arrow(masked).argminmax()
+    stored = np.frombuffer(masked.buffers()[1], dtype=np.int32)[: b.size]
+    assert got == oracle.argminmax(stored, 0)
+    # DLPack + __cuda_array_interface__
+    t = torch.from_numpy(a).cuda()
+    assert DeviceSlice.from_dlpack(t).argminmax() == oracle.argminmax(a, 0)
+
+    class Cai:
+        def __init__(self, t):
+            self.t = t
+            self.__cuda_array_interface__ = {"shape": (t.numel(),), "typestr": "<f8",
+                                             "data": (t.data_ptr(), False), "version": 3}
+    assert DeviceSlice.from_cuda_array_interface(Cai(t)).nanargminmax() == oracle.argminmax(a, 1)

@@ -23,7 +23,11 @@ def test_config2_all_dtypes_100m(dt):
     a = random_array(dt, N100M, rng)
     ds, _keep = to_device(a)
     for mode in modes_for(dt):
-        assert run_gpu(ds, mode) == oracle.argminmax(a, mode), (dt, mode)
+        got = run_gpu(ds, mode)
+        assert got == oracle.argminmax(a, mode), (dt, mode)
+        # ... and equal to the reference's dispatched SIMD path (lane-exact emulation of what
+        # an AVX-512 host computes, oracle/simd_emul.c): "scalar and SIMD" of north_star
+        assert got == oracle.simd_emul_argminmax(a, mode, 0), (dt, mode, "simd")
     if dt == "f16":  # (ii) uniform bit patterns: subnormals, -0.0, every exponent
         a = random_array(dt, N100M, rng, f16_bits=True)
         ds, _keep = to_device(a)
