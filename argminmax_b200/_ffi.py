@@ -77,6 +77,8 @@ SIGNATURES = {
     "amm_sharded_uses_nccl": (_i, [_vp]),
     "amm_sharded_uses_peer_exchange": (_i, [_vp]),
     "amm_sharded_workspace": (_i, [_vp, _i, ctypes.POINTER(_vp)]),
+    "amm_argminmax_windows": (_i, [_i, _vp, _u64, _vp, _u64, _i, _vp, _vp, _vp]),
+    "amm_argminmax_fixed_windows": (_i, [_i, _vp, _u64, _u64, _i, _vp, _vp, _vp]),
     "amm_device_count": (_i, [ctypes.POINTER(_i)]),
     "amm_device_alloc": (_i, [_i, ctypes.c_size_t, ctypes.POINTER(_vp)]),
     "amm_device_free": (_i, [_i, _vp]),

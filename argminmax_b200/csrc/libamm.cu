@@ -29,6 +29,27 @@ int launch_group4(int, amm_workspace*, ScanParams&, cudaStream_t);
 int launch_group5(int, amm_workspace*, ScanParams&, cudaStream_t);
 int launch_group6(int, amm_workspace*, ScanParams&, cudaStream_t);
 
+int windows_group0(int, amm_workspace*, const WindowParams&, uint64_t, cudaStream_t);
+int windows_group1(int, amm_workspace*, const WindowParams&, uint64_t, cudaStream_t);
+int windows_group2(int, amm_workspace*, const WindowParams&, uint64_t, cudaStream_t);
+int windows_group3(int, amm_workspace*, const WindowParams&, uint64_t, cudaStream_t);
+int windows_group4(int, amm_workspace*, const WindowParams&, uint64_t, cudaStream_t);
+int windows_group5(int, amm_workspace*, const WindowParams&, uint64_t, cudaStream_t);
+int windows_group6(int, amm_workspace*, const WindowParams&, uint64_t, cudaStream_t);
+
+static int windows_slot(int slot, amm_workspace* ws, const WindowParams& p, uint64_t mean,
+                        cudaStream_t s) {
+  switch (slot) {
+    case 0: case 4: return windows_group0(slot, ws, p, mean, s);
+    case 1: case 5: return windows_group1(slot, ws, p, mean, s);
+    case 2: case 6: return windows_group2(slot, ws, p, mean, s);
+    case 3: case 7: return windows_group3(slot, ws, p, mean, s);
+    case 8: case 9: return windows_group4(slot, ws, p, mean, s);
+    case 10: case 11: return windows_group5(slot, ws, p, mean, s);
+    default: return windows_group6(slot, ws, p, mean, s);
+  }
+}
+
 static int launch_slot(int slot, amm_workspace* ws, ScanParams& p, cudaStream_t s) {
   switch (slot) {
     case 0: case 4: return launch_group0(slot, ws, p, s);
@@ -44,6 +65,24 @@ static int launch_slot(int slot, amm_workspace* ws, ScanParams& p, cudaStream_t 
 // The kernels are instantiated in scan_inst.cu, compiled once per policy group (parallel
 // build); this is the strategy dispatch (Int / FloatIgnoreNaN / FloatReturnNaN,
 // src/dtype_strategy.rs + src/lib.rs:272-664) down to a policy slot.
+static int policy_slot(int dtype, int mode) {
+  const bool ret = (mode == AMM_RETURN_NAN);
+  switch (dtype) {
+    case AMM_I8: return 0;
+    case AMM_I16: return 1;
+    case AMM_I32: return 2;
+    case AMM_I64: return 3;
+    case AMM_U8: return 4;
+    case AMM_U16: return 5;
+    case AMM_U32: return 6;
+    case AMM_U64: return 7;
+    case AMM_F16: return ret ? 9 : 8;
+    case AMM_F32: return ret ? 11 : 10;
+    case AMM_F64: return ret ? 13 : 12;
+    default: return -1;
+  }
+}
+
 static int dispatch(amm_workspace* ws, int dtype, int mode, ScanParams& p, cudaStream_t stream) {
   const bool ret = (mode == AMM_RETURN_NAN);
   int slot;
@@ -487,6 +526,43 @@ int amm_combine_records(const amm_record* records, int count, int mode, uint64_t
   if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
   combine(records, count, mode, out);
   return AMM_OK;
+}
+
+/* ---- windowed / segmented form --------------------------------------------------------- */
+static int windows_common(int dtype, const void* dev_ptr, uint64_t n, const uint64_t* dev_offsets,
+                          uint64_t window, uint64_t n_windows, int mode, amm_workspace* ws,
+                          void* stream, uint64_t* dev_out) {
+  if (!ws || !dev_ptr || !dev_out) return AMM_ERR_ARG;
+  if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
+  const int slot = policy_slot(dtype, mode);
+  if (slot < 0) return AMM_ERR_ARG;
+  if (n == 0 || n_windows == 0) return AMM_ERR_EMPTY;
+  if (((uintptr_t)dev_ptr) % amm_dtype_size(dtype) != 0) return AMM_ERR_ALIGN;
+  int rc = set_device(ws->device);
+  if (rc) return rc;
+  WindowParams p;
+  p.base = (const uint8_t*)dev_ptr;
+  p.n = n;
+  p.offsets = dev_offsets;
+  p.window = window;
+  p.n_windows = n_windows;
+  p.out = dev_out;
+  p.mode = mode;
+  return windows_slot(slot, ws, p, n / n_windows, (cudaStream_t)stream);
+}
+
+int amm_argminmax_windows(int dtype, const void* dev_ptr, uint64_t n, const uint64_t* dev_offsets,
+                          uint64_t n_windows, int mode, amm_workspace* ws, void* stream,
+                          uint64_t* dev_out) {
+  if (!dev_offsets) return AMM_ERR_ARG;
+  return windows_common(dtype, dev_ptr, n, dev_offsets, 0, n_windows, mode, ws, stream, dev_out);
+}
+
+int amm_argminmax_fixed_windows(int dtype, const void* dev_ptr, uint64_t n, uint64_t window,
+                                int mode, amm_workspace* ws, void* stream, uint64_t* dev_out) {
+  if (window == 0) return AMM_ERR_ARG;
+  return windows_common(dtype, dev_ptr, n, nullptr, window, (n + window - 1) / window, mode, ws,
+                        stream, dev_out);
 }
 
 /* ---- device memory helpers (what DeviceSlice::from_slice needs on the Rust side) ---- */

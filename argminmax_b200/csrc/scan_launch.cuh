@@ -3,6 +3,7 @@
 #pragma once
 #include "amm_internal.h"
 #include "scan_kernel.cuh"
+#include "windows_kernel.cuh"
 
 namespace amm {
 
@@ -116,6 +117,26 @@ static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cuda
     case 5: return launch_one<P, 16, 4, true, 0, false>(ws, p, dtype_slot, 5, stream);
     default: return AMM_ERR_ARG;
   }
+}
+
+// Windowed form: warp per window for short windows, CTA per window for long ones.
+template <class P>
+static int launch_windows(amm_workspace* ws, const WindowParams& p, uint64_t mean_window,
+                          cudaStream_t stream) {
+  const uint64_t cap = (uint64_t)ws->sm_count * 8;
+  if (mean_window <= 8192) {
+    uint64_t grid = (p.n_windows + 7) / 8;  // 8 warps per CTA
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    argminmax_windows_warp_kernel<P><<<(unsigned)grid, 256, 0, stream>>>(p);
+  } else {
+    uint64_t grid = p.n_windows < cap ? p.n_windows : cap;
+    if (grid < 1) grid = 1;
+    argminmax_windows_cta_kernel<P><<<(unsigned)grid, 256, 0, stream>>>(p);
+  }
+  AMM_CUDA(cudaGetLastError());
+  ws->launches += 1;
+  return AMM_OK;
 }
 
 }  // namespace amm

@@ -175,6 +175,30 @@ class DeviceSlice:
               "amm_workspace_wait")
         return int(out[0]), int(out[1])
 
+    # --- windowed / segmented form ---------------------------
+    def argminmax_windows(self, windows, mode: int = IGNORE_NAN):
+        """(n_windows, 2) int64 CUDA tensor of absolute (argmin, argmax) per window, one launch.
+        `windows`: an int (fixed window length) or a 1-D int64/uint64 CUDA tensor of n_windows+1
+        ascending offsets.  Empty windows give -1 (AMM_NO_INDEX)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        if isinstance(windows, int):
+            nwin = -(-self.n // windows)
+            out = torch.empty((nwin, 2), dtype=torch.int64, device=dev)
+            rc = lib().amm_argminmax_fixed_windows(DTYPES[self.dtype], self.data_ptr, self.n,
+                                                   windows, mode, self.workspace.handle,
+                                                   self.stream, out.data_ptr())
+        else:
+            if windows.dim() != 1 or windows.element_size() != 8 or not windows.is_cuda:
+                raise ValueError("offsets must be a 1-D 64-bit integer CUDA tensor")
+            nwin = windows.numel() - 1
+            out = torch.empty((nwin, 2), dtype=torch.int64, device=dev)
+            rc = lib().amm_argminmax_windows(DTYPES[self.dtype], self.data_ptr, self.n,
+                                             windows.data_ptr(), nwin, mode,
+                                             self.workspace.handle, self.stream, out.data_ptr())
+        check(rc, "amm_argminmax_windows")
+        return out
+
     # --- trait ArgMinMax (src/lib.rs:134-186) ---------------------------------
     def argminmax(self) -> tuple[int, int]:
         return self._run(IGNORE_NAN)

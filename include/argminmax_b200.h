@@ -231,6 +231,23 @@ int amm_sharded_uses_peer_exchange(const amm_sharded* sh);
 /* the per-device workspace of shard g (e.g. to apply amm_workspace_set_tuning) */
 int amm_sharded_workspace(amm_sharded* sh, int g, amm_workspace** ws);
 
+/* ------------------------------------------- windowed / segmented form ("next" row) */
+/*
+ * Many sub-slices of one device array in ONE launch.  No reference entry point exists; the
+ * semantics are the reference's, composed: for every window w,
+ *     (dev_out[2w], dev_out[2w+1]) = arr[b_w .. e_w].argminmax() + b_w      (mode as above)
+ * which is what the crate's down-sampling users compute by calling `argminmax` once per bin.
+ * amm_argminmax_windows: b_w = dev_offsets[w], e_w = dev_offsets[w+1] (n_windows + 1 ascending
+ * offsets in DEVICE memory, clamped to n).  amm_argminmax_fixed_windows: b_w = w * window,
+ * ceil(n / window) windows, the last possibly short.  An empty window yields AMM_NO_INDEX
+ * twice.  Asynchronous: results land in DEVICE memory (2 * n_windows uint64) in stream order.
+ */
+int amm_argminmax_windows(int dtype, const void* dev_ptr, uint64_t n, const uint64_t* dev_offsets,
+                          uint64_t n_windows, int mode, amm_workspace* ws, void* stream,
+                          uint64_t* dev_out);
+int amm_argminmax_fixed_windows(int dtype, const void* dev_ptr, uint64_t n, uint64_t window,
+                                int mode, amm_workspace* ws, void* stream, uint64_t* dev_out);
+
 /* ------------------------------------------------------ device memory helpers */
 /* What `DeviceSlice::<T>::from_slice(&[T])` needs so that a binding does not have to link the
    CUDA runtime itself: allocate / free HBM on `device`, blocking copies in both directions. */

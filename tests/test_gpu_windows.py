@@ -1,0 +1,60 @@
+"""Windowed / segmented argmin+argmax (one launch for many sub-slices): per window the answer
+must equal the oracle's on that sub-slice (+ offset) -- the semantics of calling the
+reference's `argminmax` once per bin."""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from tests import golden_util as G
+from tests.gpu_util import modes_for, random_array, to_device
+
+pytestmark = pytest.mark.gpu
+
+
+def _expected(a, bounds, mode):
+    out = []
+    for b, e in bounds:
+        if b == e:
+            out.append((-1, -1))
+        else:
+            i, j = oracle.argminmax(a[b:e], mode)
+            out.append((i + b, j + b))
+    return out
+
+
+@pytest.mark.parametrize("dt", G.ALL_DTYPES)
+def test_fixed_windows(dt):
+    rng = np.random.default_rng(600 + G.ALL_DTYPES.index(dt))
+    n = 1_000_003
+    a = random_array(dt, n, rng)
+    if dt in G.FLOAT_DTYPES:
+        a[rng.integers(0, n, 2000)] = np.nan
+        a[5000:5600] = np.nan          # whole windows of NaN
+    ds, _keep = to_device(a, byte_offset=np.dtype(G.NP[dt]).itemsize)
+    for window in (1, 7, 100, 500, 4096, 100_000, n, 2 * n):
+        if window == 1 and dt not in ("f32", "u8"):
+            continue
+        nwin = -(-n // window)
+        bounds = [(w * window, min(n, (w + 1) * window)) for w in range(nwin)]
+        for mode in modes_for(dt):
+            got = [tuple(r) for r in ds.argminmax_windows(window, mode).cpu().tolist()]
+            if window == 1:
+                assert got == [(i, i) for i in range(n)]
+            else:
+                assert got == _expected(a, bounds, mode), (dt, window, mode)
+
+
+@pytest.mark.parametrize("dt", ["f32", "i16", "u8", "f64", "f16"])
+def test_ragged_windows_with_empty_and_duplicates(dt):
+    import torch
+    rng = np.random.default_rng(77)
+    n = 300_000
+    a = rng.integers(0, 5, n).astype(G.NP[dt])     # many ties: first occurrence per window
+    ds, _keep = to_device(a)
+    cuts = np.sort(rng.integers(0, n + 1, 2000))
+    cuts = np.concatenate([[0, 0], cuts, [n, n]])   # empty windows at both ends too
+    offs = torch.from_numpy(cuts.astype(np.int64)).cuda()
+    bounds = list(zip(cuts[:-1].tolist(), cuts[1:].tolist()))
+    for mode in modes_for(dt):
+        got = [tuple(r) for r in ds.argminmax_windows(offs, mode).cpu().tolist()]
+        assert got == _expected(a, bounds, mode)
