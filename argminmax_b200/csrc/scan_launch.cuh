@@ -124,7 +124,7 @@ template <class P>
 static int launch_windows(amm_workspace* ws, const WindowParams& p, uint64_t mean_window,
                           cudaStream_t stream) {
   const uint64_t cap = (uint64_t)ws->sm_count * 8;
-  if (mean_window <= 8192) {
+  if (mean_window <= 32768) {
     uint64_t grid = (p.n_windows + 7) / 8;  // 8 warps per CTA
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;

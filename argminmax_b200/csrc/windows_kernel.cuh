@@ -7,9 +7,7 @@
 // kernel launch per bin.  An empty window yields (AMM_NO_INDEX, AMM_NO_INDEX).
 //
 // One WARP per window (windows up to a few thousand elements: the down-sampling case) or one
-// CTA per window (large windows); exact per-element (key, index) tracking with the policies'
-// classify(), first occurrence by strict compare (indices ascend per lane) and a
-// lexicographic (key, index) shuffle reduce -- the same tie-break rule as everywhere else.
+// CTA per window (large windows).
 #pragma once
 #include "scan_kernel.cuh"
 
@@ -39,57 +37,180 @@ __device__ __forceinline__ void window_bounds(const WindowParams& p, uint64_t w,
   b = b < e ? b : e;
 }
 
-template <typename Key>
-__device__ __forceinline__ void window_store(const WindowParams& p, uint64_t w, uint64_t begin,
-                                             uint64_t end, const Best<Key>& x, int mode) {
-  uint64_t imin, imax;
-  if (begin == end) {
-    imin = imax = AMM_NO_INDEX;
-  } else if (mode == MODE_RETURN && x.pnan != POS_NONE) {
-    imin = imax = x.pnan;  // first NaN of the window for both
-  } else if (x.pmin == POS_NONE) {
-    imin = imax = begin;  // all NaN, ignore mode: the sub-slice answer is (0, 0)
-  } else {
-    imin = x.pmin;
-    imax = x.pmax;
+// ---------------------------------------------------------------------------------------
+// A window is cut into UNITS: unit 0 = the unaligned head (< one 16-byte vector, one element
+// per lane), units 1..nv = the aligned 16-byte vectors, unit nv+1 = the sub-vector tail.  The
+// fold is value-only per unit (policies.cuh, same instructions as the streaming kernel) and a
+// thread only remembers WHICH unit gave its running min / max (strict compare, ascending units
+// => earliest unit).  After the lexicographic (key, unit) reduce the winning unit -- at most 16
+// elements -- is re-read with one element per lane and a ballot picks the first match.  Cost
+// per element is that of the streaming kernel; the per-window overhead is one reduce + three
+// single-element loads.
+// ---------------------------------------------------------------------------------------
+template <class P>
+struct WindowGeom {
+  static constexpr uint32_t VE = 16 / sizeof(typename P::Elem);
+  uint64_t begin, end;  // elements
+  uint64_t a0;          // first element of unit 1 (16-byte aligned address)
+  uint32_t hc, tc;      // head / tail element counts (< VE)
+  uint64_t nv;          // aligned vectors
+  __device__ __forceinline__ WindowGeom(const uint8_t* base, uint64_t b, uint64_t e)
+      : begin(b), end(e) {
+    const uint64_t addr = (uint64_t)(uintptr_t)base + b * sizeof(typename P::Elem);
+    uint64_t head = ((16 - (addr & 15)) & 15) / sizeof(typename P::Elem);
+    const uint64_t len = e - b;
+    head = head < len ? head : len;
+    hc = (uint32_t)head;
+    a0 = b + head;
+    nv = (len - head) / VE;
+    tc = (uint32_t)(len - head - nv * VE);
   }
-  p.out[2 * w] = imin;
-  p.out[2 * w + 1] = imax;
-}
+  // element range of unit u
+  __device__ __forceinline__ void unit_range(uint64_t u, uint64_t& first, uint32_t& count) const {
+    if (u == 0) {
+      first = begin;
+      count = hc;
+    } else if (u <= nv) {
+      first = a0 + (u - 1) * VE;
+      count = VE;
+    } else {
+      first = a0 + nv * VE;
+      count = tc;
+    }
+  }
+};
 
+// value-only fold of this thread's share of the window; units are visited in ascending order
 template <class P, int STRIDE>
-__device__ __forceinline__ void window_scan(const WindowParams& p, uint64_t begin, uint64_t end,
-                                            uint32_t lane, Best<typename P::Key>& x) {
+__device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeom<P>& g,
+                                            uint32_t t, Best<typename P::Key>& x) {
   using Elem = typename P::Elem;
   using Key = typename P::Key;
-  const Elem* e = reinterpret_cast<const Elem*>(p.base);
+  const Elem* e = reinterpret_cast<const Elem*>(base);
+  auto consider = [&](Key kmin, Key kmax, bool valid, bool has_nan, uint64_t unit) {
+    if (valid && (kmin < x.kmin || x.pmin == POS_NONE)) {
+      x.kmin = kmin;
+      x.pmin = unit;
+    }
+    if (valid && (kmax > x.kmax || x.pmax == POS_NONE)) {
+      x.kmax = kmax;
+      x.pmax = unit;
+    }
+    if (has_nan && x.pnan == POS_NONE) x.pnan = unit;
+  };
+  if (t < g.hc) {  // unit 0: one head element per thread
+    Key k;
+    bool valid, is_nan;
+    P::classify(e[g.begin + t], k, valid, is_nan);
+    consider(k, k, valid, P::TRACK_NAN && is_nan, 0);
+  }
+  const uint8_t* vbase = base + g.a0 * sizeof(Elem);
   constexpr int UN = 4;
-  for (uint64_t i0 = begin + lane; i0 < end; i0 += (uint64_t)UN * STRIDE) {
-    Elem raw[UN];
+  for (uint64_t v0 = t; v0 < g.nv; v0 += (uint64_t)UN * STRIDE) {
+    uint32_t w[UN][4];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const uint64_t i = i0 + (uint64_t)u * STRIDE;
-      raw[u] = (i < end) ? e[i] : Elem(0);
+      const uint64_t v = v0 + (uint64_t)u * STRIDE;
+      if (v < g.nv) VecLoad<16>::ld(vbase + v * 16, w[u]);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
-      const uint64_t i = i0 + (uint64_t)u * STRIDE;
-      if (i < end) {
-        Key k;
-        bool valid, is_nan;
-        P::classify(raw[u], k, valid, is_nan);
-        if (valid && (k < x.kmin || x.pmin == POS_NONE)) {
-          x.kmin = k;
-          x.pmin = i;
-        }
-        if (valid && (k > x.kmax || x.pmax == POS_NONE)) {
-          x.kmax = k;
-          x.pmax = i;
-        }
-        if (P::TRACK_NAN && is_nan && x.pnan == POS_NONE) x.pnan = i;
+      const uint64_t v = v0 + (uint64_t)u * STRIDE;
+      if (v < g.nv) {
+        typename P::Acc acc;
+        P::init(acc, &w[u][0]);
+#pragma unroll
+        for (int q = P::WPI; q < 4; q += P::WPI) P::feed(acc, &w[u][q]);
+        Key kmin, kmax;
+        bool valid, has_nan;
+        P::finish(acc, kmin, kmax, valid, has_nan);
+        consider(kmin, kmax, valid, has_nan, v + 1);
       }
     }
   }
+  if (t < g.tc) {  // unit nv+1: one tail element per thread
+    Key k;
+    bool valid, is_nan;
+    P::classify(e[g.a0 + g.nv * WindowGeom<P>::VE + t], k, valid, is_nan);
+    consider(k, k, valid, P::TRACK_NAN && is_nan, g.nv + 1);
+  }
+}
+
+// One warp re-reads the winning units (one element per lane) and writes the window's answer.
+template <class P>
+__device__ __forceinline__ void window_locate_store(const WindowParams& p, uint64_t w,
+                                                    const WindowGeom<P>& g,
+                                                    const Best<typename P::Key>& x, uint32_t lane) {
+  using Elem = typename P::Elem;
+  using Key = typename P::Key;
+  const Elem* e = reinterpret_cast<const Elem*>(p.base);
+  uint64_t res[3] = {POS_NONE, POS_NONE, POS_NONE};  // min, max, first NaN
+  const uint64_t units[3] = {x.pmin, x.pmax, x.pnan};
+#pragma unroll
+  for (int c = 0; c < (P::TRACK_NAN ? 3 : 2); ++c) {
+    if (units[c] == POS_NONE) continue;  // warp-uniform
+    uint64_t first;
+    uint32_t count;
+    g.unit_range(units[c], first, count);
+    bool hit = false;
+    if (lane < count) {
+      Key k;
+      bool valid, is_nan;
+      P::classify(e[first + lane], k, valid, is_nan);
+      hit = (c == 0) ? (valid && k == x.kmin) : (c == 1) ? (valid && k == x.kmax) : is_nan;
+    }
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (m) res[c] = first + (uint64_t)(__ffs(m) - 1);
+  }
+  if (lane == 0) {
+    uint64_t imin, imax;
+    if (g.begin == g.end) {
+      imin = imax = AMM_NO_INDEX;
+    } else if (p.mode == MODE_RETURN && res[2] != POS_NONE) {
+      imin = imax = res[2];  // first NaN of the window for both
+    } else if (res[0] == POS_NONE) {
+      imin = imax = g.begin;  // all NaN, ignore mode: the sub-slice answer is (0, 0)
+    } else {
+      imin = res[0];
+      imax = res[1];
+    }
+    p.out[2 * w] = imin;
+    p.out[2 * w + 1] = imax;
+  }
+}
+
+// Warp all-reduce of the (key, unit) candidates with 32-bit unit ids (a window has fewer than
+// 2^32 units) and without the NaN field for policies that do not track NaNs: per-window cost
+// matters when windows are a few hundred elements.
+template <class P>
+__device__ __forceinline__ void window_warp_reduce(Best<typename P::Key>& x) {
+  using Key = typename P::Key;
+  Key kmin = x.kmin, kmax = x.kmax;
+  uint32_t umin = (uint32_t)x.pmin, umax = (uint32_t)x.pmax, unan = (uint32_t)x.pnan;  // NONE -> ~0u
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    const Key okmin = __shfl_xor_sync(0xFFFFFFFFu, kmin, m);
+    const Key okmax = __shfl_xor_sync(0xFFFFFFFFu, kmax, m);
+    const uint32_t oumin = __shfl_xor_sync(0xFFFFFFFFu, umin, m);
+    const uint32_t oumax = __shfl_xor_sync(0xFFFFFFFFu, umax, m);
+    if (okmin < kmin || (okmin == kmin && oumin < umin)) {
+      kmin = okmin;
+      umin = oumin;
+    }
+    if (okmax > kmax || (okmax == kmax && oumax < umax)) {
+      kmax = okmax;
+      umax = oumax;
+    }
+    if (P::TRACK_NAN) {
+      const uint32_t ounan = __shfl_xor_sync(0xFFFFFFFFu, unan, m);
+      unan = ounan < unan ? ounan : unan;
+    }
+  }
+  x.kmin = kmin;
+  x.kmax = kmax;
+  x.pmin = umin == 0xFFFFFFFFu ? POS_NONE : (uint64_t)umin;
+  x.pmax = umax == 0xFFFFFFFFu ? POS_NONE : (uint64_t)umax;
+  x.pnan = (!P::TRACK_NAN || unan == 0xFFFFFFFFu) ? POS_NONE : (uint64_t)unan;
 }
 
 // one warp per window, grid-stride over windows
@@ -102,12 +223,12 @@ __global__ void __launch_bounds__(256) argminmax_windows_warp_kernel(const Windo
        w += warps) {
     uint64_t begin, end;
     window_bounds<P>(p, w, begin, end);
+    const WindowGeom<P> g(p.base, begin, end);
     Best<Key> x;
     x.clear();
-    window_scan<P, 32>(p, begin, end, lane, x);
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) x.merge(shfl_xor(x, m));
-    if (lane == 0) window_store(p, w, begin, end, x, p.mode);
+    window_fold<P, 32>(p.base, g, lane, x);
+    window_warp_reduce<P>(x);
+    window_locate_store<P>(p, w, g, x, lane);
   }
 }
 
@@ -119,11 +240,12 @@ __global__ void __launch_bounds__(256) argminmax_windows_cta_kernel(const Window
   for (uint64_t w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
     uint64_t begin, end;
     window_bounds<P>(p, w, begin, end);
+    const WindowGeom<P> g(p.base, begin, end);
     Best<Key> x;
     x.clear();
-    window_scan<P, 256>(p, begin, end, threadIdx.x, x);
+    window_fold<P, 256>(p.base, g, threadIdx.x, x);
     x = block_reduce(x, smem);
-    if (threadIdx.x == 0) window_store(p, w, begin, end, x, p.mode);
+    if (threadIdx.x < 32) window_locate_store<P>(p, w, g, x, threadIdx.x);
   }
 }
 

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""GB/s of the windowed / segmented form for fixed window lengths (kernel-only, CUDA events)."""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+import argminmax_b200 as amm
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--bytes", type=int, default=1 << 30)
+    ap.add_argument("--dtypes", default="f32,u8,f16,f64")
+    ap.add_argument("--windows", default="64,256,1000,4096,20000,1000000")
+    ap.add_argument("--iters", type=int, default=10)
+    a = ap.parse_args()
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    t = torch.empty(a.bytes // 4, dtype=torch.int32, device="cuda:0")
+    t.random_(-2**31, 2**31 - 1, generator=g)
+    raw = t.view(torch.uint8)
+    ws = amm.Workspace(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    for dt in a.dtypes.split(","):
+        ds = amm.DeviceSlice.from_torch(raw, dtype=dt, workspace=ws, stream=stream)
+        for w in [int(x) for x in a.windows.split(",")]:
+            for _ in range(2):
+                out = ds.argminmax_windows(w)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(a.iters):
+                out = ds.argminmax_windows(w)
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / a.iters
+            print(json.dumps({"dtype": dt, "window": w, "n_windows": out.shape[0], "ms": round(ms, 4),
+                              "GBps": round(a.bytes / ms / 1e6, 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
