@@ -90,6 +90,7 @@ SIGNATURES = {
     "amm_version": (_i, []),
     "amm_workspace_set_tuning": (_i, [_vp, _i, _i, _i]),
     "amm_workspace_set_direct_threshold": (_i, [_vp, _u64]),
+    "amm_workspace_set_pipelined": (_i, [_vp, _i]),
     "amm_workspace_get_tuning": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i),
                                       ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "amm_variant_count": (_i, []),

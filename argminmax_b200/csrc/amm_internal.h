@@ -45,6 +45,8 @@ struct amm_workspace {
   amm_record* rec_host_dev;  // ... its device address
   uint64_t seq;              // calls issued on this workspace
   int publish_fence;
+  int pdl;        // launch scans with programmatic stream serialization (AMM_PDL=0 disables)
+  int pipelined;  // let a scan's streaming phase overlap the previous scan's tail
   int last_grid, last_threads;
   uint64_t launches;
   amm_host_pipeline* pipe;  // lazily created by amm_host_argminmax

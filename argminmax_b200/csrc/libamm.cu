@@ -161,6 +161,7 @@ int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global
   p.seq = ++ws->seq;
   p.mode = mode;
   p.publish_fence = ws->publish_fence;
+  p.pipelined = (ws->pdl && ws->pipelined) ? 1 : 0;
   if (exchange) {
     p.world = ws->xworld;
     p.rank = ws->xrank;
@@ -305,6 +306,7 @@ static int workspace_init(amm_workspace* ws, int device) {
     ws->direct_threads = 256;
   if (ws->direct_ctas_per_sm < 1 || ws->direct_ctas_per_sm > 32) ws->direct_ctas_per_sm = 2;
   ws->publish_fence = getenv("AMM_PUBLISH_FENCE") ? atoi(getenv("AMM_PUBLISH_FENCE")) : 0;
+  ws->pdl = getenv("AMM_PDL") ? atoi(getenv("AMM_PDL")) : 1;
   ws->max_grid = ws->sm_count * 32;
   // partials sized for the widest Best<int64_t> (40 B) -> 64 B slots
   AMM_CUDA(cudaMalloc(&ws->partials, (size_t)ws->max_grid * 64));
@@ -637,6 +639,12 @@ int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, in
   ws->threads = threads > 0 ? threads : 0;
   ws->ctas_per_sm = ctas_per_sm > 0 ? ctas_per_sm : 0;
   ws->variant = variant >= 0 ? variant : -1;
+  return AMM_OK;
+}
+
+int amm_workspace_set_pipelined(amm_workspace* ws, int on) {
+  if (!ws) return AMM_ERR_ARG;
+  ws->pipelined = on ? 1 : 0;
   return AMM_OK;
 }
 

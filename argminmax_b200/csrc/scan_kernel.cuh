@@ -59,6 +59,7 @@ struct ScanParams {
   uint64_t seq;
   int mode;
   int publish_fence;  // debug: also issue a system-scope fence after publishing
+  int pipelined;      // 1: the streaming phase may overlap the previous grid's tail (PDL)
   // ---- fused cross-GPU exchange (world > 1): see finalize()
   int world;                   // ranks taking part in this logical call (1 = none)
   int rank;                    // this GPU's position (ascending shard order)
@@ -482,12 +483,28 @@ __device__ __forceinline__ void finalize(const ScanParams& p, const Best<Key>& x
   }
 }
 
+// Programmatic dependent launch (PDL).  Scans are launched with the programmatic-stream-
+// serialization attribute and every CTA signals launch_dependents on entry, so the NEXT scan
+// on the stream can be scheduled while this one drains.  Default (safe) mode: a CTA executes
+// griddepcontrol.wait before its first global load, i.e. only launch latency is hidden.
+// Pipelined mode (amm_workspace_set_pipelined, caller promises that a scan's input is not
+// produced by the kernel right before it on the stream): the wait moves to the point where
+// the CTA first touches the shared workspace (partials, ticket, record slots), so the
+// STREAMING phase of scan k+1 overlaps the fold / locate / publish tail of scan k.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_prior_grid() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // Cross-CTA reduce: every CTA deposits its Best, the last one to arrive (ticket) folds them.
 // Returns true in the last CTA only, with `b` = grid-wide result.  gridDim.x == 1 skips the
 // round trip through global memory.
 template <typename Key>
 __device__ __forceinline__ bool grid_reduce(const ScanParams& p, Best<Key>& b, Best<Key>* smem,
                                             uint32_t* s_is_last) {
+  pdl_wait_prior_grid();  // from here on the workspace is ours
   if (gridDim.x == 1) return true;
   Best<Key>* partials = reinterpret_cast<Best<Key>*>(p.partials);
   if (threadIdx.x == 0) {
@@ -528,6 +545,8 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
   constexpr int VE = VEC / sizeof(typename P::Elem);
   __shared__ Best<Key> smem[32];
   __shared__ uint32_t s_is_last;
+  pdl_launch_dependents();
+  if (!p.pipelined) pdl_wait_prior_grid();
   const uint8_t* main_base = p.base + p.head_elems * sizeof(typename P::Elem);
   const Bounds bd(p);
   // contiguous slice of whole vectors per CTA, coalesced 128-bit loads, UN in flight
@@ -586,6 +605,8 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   constexpr int NW = VL::NW;
   __shared__ Best<Key> smem[32];
   __shared__ uint32_t s_is_last;
+  pdl_launch_dependents();
+  if (!p.pipelined) pdl_wait_prior_grid();
 
   const uint32_t tile_vecs = blockDim.x * U;
   const uint64_t tile_bytes = (uint64_t)tile_vecs * VEC;

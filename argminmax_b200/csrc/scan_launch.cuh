@@ -1,6 +1,8 @@
 // scan_launch.cuh -- host-side launch geometry for the scan kernels (included by the
 // per-policy-group translation units, scan_inst.cu).
 #pragma once
+#include <string.h>
+
 #include "amm_internal.h"
 #include "scan_kernel.cuh"
 #include "windows_kernel.cuh"
@@ -22,6 +24,24 @@ static const VariantDesc kVariants[] __attribute__((unused)) = {
     {16, 4, 1, 0, "v16x4_pf_nohint"},  // 5: as 0 without the .L2::256B prefetch-size hint
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_* in scan_kernel.cuh).
+template <typename Kernel>
+static cudaError_t launch_scan(Kernel kernel, unsigned grid, unsigned threads, cudaStream_t stream,
+                               const ScanParams& p, bool pdl) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
 
 template <class P, int VEC, int U, bool PF, int HINT, bool XCHG>
 static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
@@ -55,8 +75,7 @@ static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int vari
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
   if (grid > (uint64_t)ws->max_grid) grid = (uint64_t)ws->max_grid;
-  kernel<<<(unsigned)grid, threads, 0, stream>>>(p);
-  AMM_CUDA(cudaGetLastError());
+  AMM_CUDA(launch_scan(kernel, (unsigned)grid, (unsigned)threads, stream, p, ws->pdl != 0));
   ws->last_grid = (int)grid;
   ws->last_threads = threads;
   ws->launches += 1;
@@ -81,10 +100,11 @@ static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) 
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   if (p.world > 1)
-    argminmax_direct_kernel<P, true><<<(unsigned)grid, threads, 0, stream>>>(p);
+    AMM_CUDA(launch_scan(argminmax_direct_kernel<P, true>, (unsigned)grid, (unsigned)threads, stream,
+                         p, ws->pdl != 0));
   else
-    argminmax_direct_kernel<P, false><<<(unsigned)grid, threads, 0, stream>>>(p);
-  AMM_CUDA(cudaGetLastError());
+    AMM_CUDA(launch_scan(argminmax_direct_kernel<P, false>, (unsigned)grid, (unsigned)threads,
+                         stream, p, ws->pdl != 0));
   ws->last_grid = (int)grid;
   ws->last_threads = threads;
   ws->launches += 1;

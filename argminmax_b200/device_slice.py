@@ -58,6 +58,11 @@ class Workspace:
         check(lib().amm_workspace_set_tuning(self._h, threads, ctas_per_sm, variant),
               "amm_workspace_set_tuning")
 
+    def set_pipelined(self, on: bool = True):
+        """Let consecutive scans on one stream overlap (see amm_workspace_set_pipelined)."""
+        check(lib().amm_workspace_set_pipelined(self._h, 1 if on else 0),
+              "amm_workspace_set_pipelined")
+
     def set_direct_threshold(self, nbytes: int):
         check(lib().amm_workspace_set_direct_threshold(self._h, nbytes),
               "amm_workspace_set_direct_threshold")

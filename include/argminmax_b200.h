@@ -269,6 +269,12 @@ int amm_version(void);                /* AMM_VERSION_MAJOR * 100 + AMM_VERSION_M
    ctas_per_sm <= 0 and variant < 0 select "automatic" for that knob.  get_tuning reports what
    the most recent streaming launch actually used. */
 int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, int variant);
+/* Pipelined mode for back-to-back scans on one stream (many resident arrays, repeated scans):
+   the streaming phase of scan k+1 may start while scan k's last CTA is still folding /
+   publishing (programmatic dependent launch).  The caller promises that the input of a scan is
+   NOT produced by the kernel enqueued immediately before it on the same stream (memcpys and
+   earlier kernels are fine).  Off by default; results and their order are unchanged. */
+int amm_workspace_set_pipelined(amm_workspace* ws, int on);
 /* Inputs of at most `bytes` take the one-pass latency kernel (exact per-element tracking, no
    second phase) instead of the streaming kernel; 0 disables it. */
 int amm_workspace_set_direct_threshold(amm_workspace* ws, uint64_t bytes);

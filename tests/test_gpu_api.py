@@ -180,3 +180,41 @@ def test_arrow_and_dlpack_adapters():
             self.__cuda_array_interface__ = {"shape": (t.numel(),), "typestr": "<f8",
                                              "data": (t.data_ptr(), False), "version": 3}
     assert DeviceSlice.from_cuda_array_interface(Cai(t)).nanargminmax() == oracle.argminmax(a, 1)
+
+
+def test_pipelined_back_to_back_scans_keep_every_result():
+    """Pipelined mode (PDL: the streaming phase of scan k+1 overlaps the tail of scan k on the
+    same workspace): every call must still deliver its own record, in order."""
+    import torch
+
+    from argminmax_b200 import AmmRecord, DTYPES, Workspace, lib
+    L = lib()
+    rng = np.random.default_rng(202)
+    arrays = [random_array("f32", n, rng) for n in (5_000_011, 3_000_000, 12_345, 9_999_999, 64, 2_500_001)]
+    arrays.append(random_array("u8", 20_000_003, rng).view(np.uint8))
+    expected = [oracle.argminmax(a, 0) for a in arrays]
+    devs = [to_device(a) for a in arrays]
+    for pipelined in (True, False):
+        ws = Workspace(0)
+        ws.set_pipelined(pipelined)
+        s = torch.cuda.Stream()
+        reps = 6
+        recs = torch.zeros((reps * len(arrays), 64), dtype=torch.uint8, device="cuda:0")
+        with torch.cuda.stream(s):
+            k = 0
+            for _ in range(reps):
+                for (ds, _keep), a in zip(devs, arrays):
+                    rc = L.amm_argminmax_launch(DTYPES[ds.dtype], ds.data_ptr, ds.n, 0, 0, ws.handle,
+                                                s.cuda_stream, recs[k].data_ptr())
+                    assert rc == 0
+                    k += 1
+        s.synchronize()
+        raw = recs.cpu().numpy().tobytes()
+        for k in range(reps * len(arrays)):
+            r = AmmRecord.from_buffer_copy(raw[64 * k:64 * k + 64])
+            assert (r.min_idx, r.max_idx) == expected[k % len(arrays)], (pipelined, k)
+            assert r.seq == k + 1
+        out = (ctypes.c_uint64 * 2)()
+        assert L.amm_workspace_wait(ws.handle, s.cuda_stream, 0, out) == 0
+        assert (out[0], out[1]) == expected[-1]
+        ws.close()

@@ -14,9 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_no_out_of_bounds_loads():
     from argminmax_b200 import _build
-    dbg = _build.DEBUG_LIB_PATH
-    if not os.path.exists(dbg):
-        dbg = _build.build_boundscheck()
+    dbg = _build.build_boundscheck()  # no-op when the in-tree debug twin is current
     env = dict(os.environ, AMM_LIB_PATH=dbg, AMM_HOST_CHUNK_MB="1")
     proc = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sanitize_case.py")],
                           capture_output=True, text=True, timeout=900, env=env)
@@ -47,7 +45,7 @@ def test_bounds_check_build_detects_a_violation(tmp_path):
     """The checker itself works: with AMM_DEBUG_SHRINK_BYTES the debug build is told that the
     array ends 4 bytes early while the kernels still scan all of it -- every call must fail."""
     from argminmax_b200 import _build
-    dbg = _build.DEBUG_LIB_PATH if os.path.exists(_build.DEBUG_LIB_PATH) else _build.build_boundscheck()
+    dbg = _build.build_boundscheck()
     script = tmp_path / "selftest.py"
     script.write_text(_SELFTEST.format(root=ROOT))
     env = dict(os.environ, AMM_LIB_PATH=dbg, AMM_DEBUG_SHRINK_BYTES="4")

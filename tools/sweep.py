@@ -48,6 +48,7 @@ def main():
     data = make_data(a.dtype, a.n)
     ws = amm.Workspace(0)
     ws.set_direct_threshold(0)  # this tool sweeps the streaming kernel only
+    ws.set_pipelined(bool(int(os.environ.get("AMM_PIPELINED", "0"))))
     copies = [data] + [data.clone() for _ in range(a.rotate - 1)]
     dss = [amm.DeviceSlice.from_torch(c, dtype=a.dtype, workspace=ws,
                                       stream=torch.cuda.current_stream().cuda_stream) for c in copies]
