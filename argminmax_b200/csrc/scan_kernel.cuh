@@ -14,20 +14,19 @@
 //    issued before the current tile is folded, so every thread keeps 2 x U vectors
 //    in flight.
 //  * Per element the thread only folds a VALUE-ONLY min and max (policies.cuh).
-//    Per TILE it compares the tile's (min key, max key) with its running pair and
-//    remembers the TILE ID of the winner (strict compare, tiles visited in
-//    ascending order => earliest tile per thread).  No index lanes, hence no index
-//    overflow and none of the reference's restart loop; the loop is branch-free and
-//    its cost does not depend on the data order.
+//    Per VECTOR (16 or 32 bytes) it compares the vector's (min key, max key) with its
+//    running pair and remembers WHICH vector won (a 32-bit slot id; strict compare,
+//    vectors visited in ascending order => earliest vector per thread).  No index
+//    lanes, hence no index overflow and none of the reference's restart loop; the loop
+//    is branch-free and its cost does not depend on the data order.
 //  * CTA reduce (warp shuffles, then shared memory) and the cross-CTA reduce
-//    (last-block-done ticket) are lexicographic on (key, tile): the earliest tile
-//    that contains the global extreme wins.
-//  * The last CTA then runs an EXACT lexicographic (key, index) scan over at most
-//    five small element ranges: the winning min tile, the winning max tile, the
-//    first tile that holds a NaN (return-NaN mode), and the unaligned head and the
-//    sub-vector tail of the array.  That yields first-occurrence indices with the
-//    reference's tie-break rule (src/simd/task.rs:273,290) and re-reads at most
-//    3 tiles (<= ~200 KB, L2-resident) of an arbitrarily large input.
+//    (last-block-done ticket) are lexicographic on (key, global vector index): the
+//    earliest vector that contains the global extreme wins.
+//  * One warp of the last CTA finishes exactly: the winning min / max / first-NaN
+//    vectors (<= 32 elements each) are re-read with one element per lane and a ballot
+//    picks the first match; the unaligned head and the sub-vector tail of the array
+//    ride along as per-lane candidates.  That yields first-occurrence indices with the
+//    reference's tie-break rule (src/simd/task.rs:273,290) and re-reads < 200 bytes.
 //  * One 64-byte record (keys, global indices, first NaN, flags) is written to the
 //    workspace's device slot and to a pinned host slot: one launch, no memcpy.
 #pragma once
@@ -196,40 +195,42 @@ struct VecLoad<32, HINT> {
   }
 };
 
-// Running per-thread state of the streaming phase (tile ids are 32-bit here).
+// Running per-thread state of the streaming phase.  A SLOT is one vector position of one tile:
+// slot = tile * U + j (32-bit); together with the thread id it names one global vector:
+//   vector index = tile * (blockDim * U) + j * blockDim + tid,
+// and vector index order IS address order, so a lexicographic reduce on (key, vector index)
+// finds the vector that holds the first occurrence of the extreme.
 template <typename Key>
 struct Running {
   Key kmin, kmax;
-  uint32_t tmin, tmax, tnan;
+  uint32_t smin, smax, snan;
 };
 
 template <class P, int NW, int U>
-__device__ __forceinline__ void fold_tile(const uint32_t (&v)[U][NW], uint32_t tile_id,
+__device__ __forceinline__ void fold_tile(const uint32_t (&v)[U][NW], uint32_t tile0,
                                           Running<typename P::Key>& r) {
   using Key = typename P::Key;
-  typename P::Acc acc;
-  P::init(acc, &v[0][0]);
 #pragma unroll
   for (int j = 0; j < U; ++j) {
+    typename P::Acc acc;
+    P::init(acc, &v[j][0]);
 #pragma unroll
-    for (int w = 0; w < NW; w += P::WPI) {
-      if (j == 0 && w == 0) continue;
-      P::feed(acc, &v[j][w]);
-    }
+    for (int w = P::WPI; w < NW; w += P::WPI) P::feed(acc, &v[j][w]);
+    Key kmin, kmax;
+    bool valid, has_nan;
+    P::finish(acc, kmin, kmax, valid, has_nan);
+    // slots arrive in ascending order per thread, so "strictly better, or nothing yet" IS the
+    // lexicographic (key, slot) update: earliest vector per thread, no branches.
+    const uint32_t slot = tile0 * U + j;
+    const bool first = (r.smin == TILE_NONE);
+    const bool um = valid && (first || kmin < r.kmin);
+    const bool uM = valid && (first || kmax > r.kmax);
+    r.kmin = um ? kmin : r.kmin;
+    r.smin = um ? slot : r.smin;
+    r.kmax = uM ? kmax : r.kmax;
+    r.smax = uM ? slot : r.smax;
+    r.snan = (has_nan && r.snan == TILE_NONE) ? slot : r.snan;
   }
-  Key kmin, kmax;
-  bool valid, has_nan;
-  P::finish(acc, kmin, kmax, valid, has_nan);
-  // tiles arrive in ascending order per thread, so "strictly better, or nothing yet"
-  // IS the lexicographic (key, tile) update.
-  const bool first = (r.tmin == TILE_NONE);
-  const bool um = valid && (first || kmin < r.kmin);
-  const bool uM = valid && (first || kmax > r.kmax);
-  r.kmin = um ? kmin : r.kmin;
-  r.tmin = um ? tile_id : r.tmin;
-  r.kmax = uM ? kmax : r.kmax;
-  r.tmax = uM ? tile_id : r.tmax;
-  r.tnan = (has_nan && r.tnan == TILE_NONE) ? tile_id : r.tnan;
 }
 
 // Exact (key, index) scan of elements [begin, end) by the whole CTA, 4 independent loads
@@ -287,46 +288,6 @@ __device__ __forceinline__ typename P::Elem vec_elem(const uint32_t (&w)[NW], in
   if (sizeof(Elem) == 2) return (Elem)((w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu);
   if (sizeof(Elem) == 4) return (Elem)w[e];
   return (Elem)(((uint64_t)w[2 * e + 1] << 32) | (uint64_t)w[2 * e]);
-}
-
-// Exact lexicographic (key, index) scan of ONE streaming tile (0-based id `tile0`) with the
-// same vector loads and thread->vector mapping as the streaming phase: one round trip to
-// memory for the whole tile.
-template <class P, int VEC, int U>
-__device__ __forceinline__ void exact_tile(const Bounds& bd, const uint8_t* main_base,
-                                           uint64_t head_elems, uint64_t tile0, uint64_t n_vec,
-                                           Best<typename P::Key>& b) {
-  using Key = typename P::Key;
-  constexpr int NW = VecLoad<VEC>::NW;
-  constexpr int VE = VEC / sizeof(typename P::Elem);
-  const uint64_t v0 = tile0 * ((uint64_t)blockDim.x * U) + threadIdx.x;
-  uint32_t w[U][NW];
-#pragma unroll
-  for (int j = 0; j < U; ++j) {
-    const uint64_t vi = v0 + (uint64_t)j * blockDim.x;
-    if (vi < n_vec) {
-      bd.check(main_base + vi * VEC, VEC);
-      VecLoad<VEC>::ld(main_base + vi * VEC, w[j]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < U; ++j) {
-    const uint64_t vi = v0 + (uint64_t)j * blockDim.x;
-    if (vi < n_vec) {
-      const uint64_t i0 = head_elems + vi * VE;
-#pragma unroll
-      for (int e = 0; e < VE; ++e) {
-        Key k;
-        bool valid, is_nan;
-        P::classify(vec_elem<P, NW>(w[j], e), k, valid, is_nan);
-        if (valid) {
-          b.merge_min(k, i0 + e);
-          b.merge_max(k, i0 + e);
-        }
-        if (P::TRACK_NAN && is_nan && i0 + e < b.pnan) b.pnan = i0 + e;
-      }
-    }
-  }
 }
 
 // Publish one record to the device slot and (if mapped) the pinned host slot.
@@ -601,6 +562,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
 template <class P, int VEC, int U, bool PREFETCH, int HINT, bool XCHG>
 __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanParams p) {
   using VL = VecLoad<VEC, HINT>;
+  constexpr uint32_t VEC_ELEMS = VEC / sizeof(typename P::Elem);
   using Key = typename P::Key;
   constexpr int NW = VL::NW;
   __shared__ Best<Key> smem[32];
@@ -616,7 +578,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   Running<Key> run;
   run.kmin = KeyLim<Key>::MAXV;
   run.kmax = KeyLim<Key>::MINV;
-  run.tmin = run.tmax = run.tnan = TILE_NONE;
+  run.smin = run.smax = run.snan = TILE_NONE;
 
   // ------------------------------------------------ streaming phase: full tiles
   // Two register buffers in ping-pong: the loads of the next tile are in flight
@@ -647,7 +609,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
             VL::ld(q + j * jstride, b[j]);
           }
         }
-        fold_tile<P, NW, U>(a, t + 1, run);
+        fold_tile<P, NW, U>(a, t, run);
         if (t1 >= nft) break;
         const uint32_t t2 = t1 + gridDim.x;
         if (t2 < nft) {
@@ -658,7 +620,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
           VL::ld(q + j * jstride, a[j]);
         }
         }
-        fold_tile<P, NW, U>(b, t1 + 1, run);
+        fold_tile<P, NW, U>(b, t1, run);
         t = t2;
       }
     } else {
@@ -669,7 +631,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
           bd.check(q + j * jstride, VEC);
           VL::ld(q + j * jstride, a[j]);
         }
-        fold_tile<P, NW, U>(a, t + 1, run);
+        fold_tile<P, NW, U>(a, t, run);
       }
     }
   }
@@ -690,37 +652,87 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
         for (int w = 0; w < NW; ++w) cur[j][w] = cur[0][w];
       }
     }
-    fold_tile<P, NW, U>(cur, p.n_full_tiles + 1, run);
+    fold_tile<P, NW, U>(cur, p.n_full_tiles, run);
   }
 
-  // ------------------------------------------- CTA reduce on (key, tile id)
+  // ------------------------------- CTA reduce on (key, global vector index)
+  auto slot_to_vec = [&](uint32_t slot) -> uint64_t {
+    return slot == TILE_NONE ? POS_NONE
+                             : (uint64_t)(slot / U) * tile_vecs + (uint64_t)(slot % U) * blockDim.x +
+                                   threadIdx.x;
+  };
   Best<Key> b;
   b.kmin = run.kmin;
   b.kmax = run.kmax;
-  b.pmin = run.tmin == TILE_NONE ? POS_NONE : (uint64_t)run.tmin;
-  b.pmax = run.tmax == TILE_NONE ? POS_NONE : (uint64_t)run.tmax;
-  b.pnan = run.tnan == TILE_NONE ? POS_NONE : (uint64_t)run.tnan;
+  b.pmin = slot_to_vec(run.smin);
+  b.pmax = slot_to_vec(run.smax);
+  b.pnan = slot_to_vec(run.snan);
   b = block_reduce(b, smem);
 
   // ------------------------------------------- last-block-done grid finalise
   if (!grid_reduce(p, b, smem, &s_is_last)) return;
-  const Best<Key> g = b;
 
-  // ------------------- exact (key, index) scan of the few candidate ranges
-  Best<Key> x;
-  x.clear();
-  exact_range<P, false>(bd, p.base, 0, p.head_elems, x);
-  exact_range<P, false>(bd, p.base, p.tail_start, p.n, x);
-  const uint64_t cand[3] = {g.pmin, g.pmax, g.pnan};
+  // ------- exact finish by ONE warp: the winning vectors (<= 32 elements each) are re-read
+  // with one element per lane and a ballot picks the first match; the unaligned head and the
+  // sub-vector tail (< one vector each) ride along as exact per-lane candidates.
+  __shared__ Best<Key> s_final;
+  if (threadIdx.x < 32) {
+    using Elem = typename P::Elem;
+    const Elem* e = reinterpret_cast<const Elem*>(p.base);
+    const uint32_t lane = threadIdx.x;
+    Best<Key> x;
+    x.clear();
+    const uint64_t cand[3] = {b.pmin, b.pmax, b.pnan};
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const uint64_t tid = cand[c];
-    if (tid == POS_NONE) continue;
-    if (c == 1 && tid == cand[0]) continue;
-    if (c == 2 && (tid == cand[0] || tid == cand[1])) continue;
-    exact_tile<P, VEC, U>(bd, main_base, p.head_elems, tid - 1, p.n_vec, x);
+    for (int c = 0; c < (P::TRACK_NAN ? 3 : 2); ++c) {
+      if (cand[c] == POS_NONE) continue;  // warp-uniform
+      const uint64_t first = p.head_elems + cand[c] * VEC_ELEMS;
+      bool hit = false;
+      if (lane < VEC_ELEMS) {
+        Key k;
+        bool valid, is_nan;
+        bd.check(&e[first + lane], sizeof(Elem));
+        P::classify(e[first + lane], k, valid, is_nan);
+        hit = (c == 0) ? (valid && k == b.kmin) : (c == 1) ? (valid && k == b.kmax) : is_nan;
+      }
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+      if (m != 0 && lane == 0) {
+        const uint64_t idx = first + (uint64_t)(__ffs(m) - 1);
+        if (c == 0) {
+          x.kmin = b.kmin;
+          x.pmin = idx;
+        } else if (c == 1) {
+          x.kmax = b.kmax;
+          x.pmax = idx;
+        } else {
+          x.pnan = idx;
+        }
+      }
+    }
+    // head: elements [0, head_elems); tail: [tail_start, n); both shorter than one vector
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+      const uint64_t begin = part == 0 ? 0 : p.tail_start;
+      const uint64_t end = part == 0 ? p.head_elems : p.n;
+      const uint64_t i = begin + lane;
+      if (i < end) {
+        Key k;
+        bool valid, is_nan;
+        bd.check(&e[i], sizeof(Elem));
+        P::classify(e[i], k, valid, is_nan);
+        if (valid) {
+          x.merge_min(k, i);
+          x.merge_max(k, i);
+        }
+        if (P::TRACK_NAN && is_nan && i < x.pnan) x.pnan = i;
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) x.merge(shfl_xor(x, m));
+    if (lane == 0) s_final = x;
   }
-  x = block_reduce(x, smem);
+  __syncthreads();
+  const Best<Key> x = s_final;
 
   finalize<XCHG>(p, x);
 }

@@ -66,7 +66,7 @@ static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int vari
   p.n_vec = (p.n - head) / vec_elems;
   p.tail_start = head + p.n_vec * vec_elems;
   const uint64_t full = p.n_vec / tile_vecs;
-  if (full >= 0xFFFFFFFEull) return AMM_ERR_TOO_LARGE;
+  if ((full + 2) * (uint64_t)U >= 0xFFFFFFFFull) return AMM_ERR_TOO_LARGE;  // 32-bit slot ids
   p.n_full_tiles = (uint32_t)full;
   p.rem_vecs = (uint32_t)(p.n_vec % tile_vecs);
   const uint64_t tiles = full + (p.rem_vecs ? 1 : 0);
