@@ -295,7 +295,7 @@ static int workspace_init(amm_workspace* ws, int device) {
   ws->threads = 0;      // automatic
   ws->ctas_per_sm = 0;  // automatic
   ws->variant = -1;     // automatic
-  ws->direct_bytes = (uint64_t)8 << 20;
+  ws->direct_bytes = (uint64_t)8 << 10;
   ws->direct_threads = 256;
   ws->direct_ctas_per_sm = 2;
   // experiment knobs (tools/, profiling); the defaults are the tuned values
