@@ -59,6 +59,30 @@ struct amm_workspace {
 };
 
 namespace amm {
+// Every public entry point leaves the caller's current CUDA device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  int rc = AMM_OK;
+  explicit DeviceGuard(int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) {
+      rc = AMM_ERR_CUDA;
+      return;
+    }
+    if (cur != device) {
+      if (cudaSetDevice(device) != cudaSuccess) {
+        rc = AMM_ERR_CUDA;
+        return;
+      }
+      prev = cur;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 int set_device(int device);
 int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global_offset,
            amm_workspace* ws, cudaStream_t stream, void* dev_record_out, bool exchange = false);

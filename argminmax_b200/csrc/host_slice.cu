@@ -65,8 +65,10 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
   if (dtype < 0 || dtype >= AMM_DTYPE_COUNT) return AMM_ERR_ARG;
   if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
   if (n == 0) return AMM_ERR_EMPTY;
-  int rc = set_device(ws->device);
-  if (rc) return rc;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   if (!ws->pipe) {
     rc = pipeline_create(ws);
     if (rc) {

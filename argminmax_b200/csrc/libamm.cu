@@ -139,8 +139,10 @@ int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global
   }
   const size_t es = amm_dtype_size(dtype);
   if (((uintptr_t)dev_ptr) % es != 0) return AMM_ERR_ALIGN;
-  int rc = set_device(ws->device);
-  if (rc) return rc;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   ScanParams p;
   memset(&p, 0, sizeof(p));
   p.base = (const uint8_t*)dev_ptr;
@@ -277,8 +279,10 @@ int amm_combine_records_launch(const void* dev_records, int count, int mode, amm
                                void* stream) {
   if (!dev_records || !ws || count < 1) return AMM_ERR_ARG;
   if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
-  int rc = set_device(ws->device);
-  if (rc) return rc;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   combine_records_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
       (const amm_record*)dev_records, count, mode, ws->rec_dev, ws->rec_host_dev, ++ws->seq);
   AMM_CUDA(cudaGetLastError());
@@ -327,8 +331,10 @@ int amm_workspace_create(int device, amm_workspace** out) {
   int count = 0;
   AMM_CUDA(cudaGetDeviceCount(&count));
   if (device < 0 || device >= count) return AMM_ERR_ARG;
-  int rc = set_device(device);
-  if (rc) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   amm_workspace* ws = new (std::nothrow) amm_workspace();
   if (!ws) return AMM_ERR_ARG;
   rc = workspace_init(ws, device);
@@ -344,7 +350,7 @@ int amm_workspace_create(int device, amm_workspace** out) {
 
 int amm_workspace_destroy(amm_workspace* ws) {
   if (!ws) return AMM_OK;
-  set_device(ws->device);
+  DeviceGuard guard(ws->device);
   host_pipeline_destroy(ws);
   exchange_destroy(ws);
   if (ws->partials) cudaFree(ws->partials);
@@ -364,8 +370,10 @@ int amm_argminmax_launch(int dtype, const void* dev_ptr, uint64_t n, int mode,
 /* ---- fused cross-GPU exchange: setup ------------------------------------------------- */
 int amm_exchange_create(amm_workspace* ws, int world, int rank, void* ipc_handle_out) {
   if (!ws || world < 2 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return AMM_ERR_ARG;
-  int rc = set_device(ws->device);
-  if (rc) return rc;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   exchange_destroy(ws);
   const size_t bytes = (size_t)2 * world * XCHG_SLOT_WORDS * sizeof(uint64_t);
   AMM_CUDA(cudaMalloc((void**)&ws->xbuf, bytes));
@@ -398,8 +406,10 @@ static int exchange_upload(amm_workspace* ws, uint64_t** table) {
 
 int amm_exchange_connect_ipc(amm_workspace* ws, const void* ipc_handles) {
   if (!ws || !ipc_handles || ws->xworld < 2) return AMM_ERR_ARG;
-  int rc = set_device(ws->device);
-  if (rc) return rc;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   uint64_t* table[XCHG_MAX_WORLD];
   for (int r = 0; r < ws->xworld; ++r) {
     if (r == ws->xrank) {
@@ -418,8 +428,10 @@ int amm_exchange_connect_ipc(amm_workspace* ws, const void* ipc_handles) {
 
 int amm_exchange_connect_ptrs(amm_workspace* ws, void* const* peer_buffers) {
   if (!ws || !peer_buffers || ws->xworld < 2) return AMM_ERR_ARG;
-  int rc = set_device(ws->device);
-  if (rc) return rc;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   uint64_t* table[XCHG_MAX_WORLD];
   for (int r = 0; r < ws->xworld; ++r) table[r] = (uint64_t*)peer_buffers[r];
   table[ws->xrank] = ws->xbuf;
@@ -435,6 +447,9 @@ int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2
   if (!ws || !out) return AMM_ERR_ARG;
   if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
   if (ws->seq == 0) return AMM_ERR_ARG;  // nothing was ever launched on this workspace
+  // `stream` may be NULL = the default stream OF THE CURRENT DEVICE: make that the workspace's
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
   // The kernel publishes the record into pinned host memory and writes `seq` last (after a
   // system-scope fence), so the host can pick the answer up by polling that word -- a few
   // microseconds sooner than cudaStreamSynchronize returns.  The stream is queried now and
@@ -540,8 +555,10 @@ static int windows_common(int dtype, const void* dev_ptr, uint64_t n, const uint
   if (slot < 0) return AMM_ERR_ARG;
   if (n == 0 || n_windows == 0) return AMM_ERR_EMPTY;
   if (((uintptr_t)dev_ptr) % amm_dtype_size(dtype) != 0) return AMM_ERR_ALIGN;
-  int rc = set_device(ws->device);
-  if (rc) return rc;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   WindowParams p;
   p.base = (const uint8_t*)dev_ptr;
   p.n = n;
@@ -576,29 +593,37 @@ int amm_device_count(int* count) {
 
 int amm_device_alloc(int device, size_t bytes, void** dev_ptr) {
   if (!dev_ptr) return AMM_ERR_ARG;
-  int rc = set_device(device);
-  if (rc) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   AMM_CUDA(cudaMalloc(dev_ptr, bytes ? bytes : 1));
   return AMM_OK;
 }
 
 int amm_device_free(int device, void* dev_ptr) {
-  int rc = set_device(device);
-  if (rc) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   AMM_CUDA(cudaFree(dev_ptr));
   return AMM_OK;
 }
 
 int amm_copy_to_device(int device, void* dst_dev, const void* src_host, size_t bytes) {
-  int rc = set_device(device);
-  if (rc) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   AMM_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
   return AMM_OK;
 }
 
 int amm_copy_to_host(int device, void* dst_host, const void* src_dev, size_t bytes) {
-  int rc = set_device(device);
-  if (rc) return rc;
+  DeviceGuard guard(device);
+  if (guard.rc) return guard.rc;
+  int rc = AMM_OK;
+  (void)rc;
   AMM_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
   return AMM_OK;
 }

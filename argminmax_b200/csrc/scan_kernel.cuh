@@ -37,7 +37,7 @@
 
 namespace amm {
 
-constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;
+constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;  // "no slot yet" in the per-thread running state
 constexpr uint64_t POS_NONE = 0xFFFFFFFFFFFFFFFFull;
 constexpr int MAX_THREADS = 512;
 
@@ -66,7 +66,7 @@ struct ScanParams {
   uint64_t xseq;               // exchange sequence number, identical on all ranks
 };
 
-// Debug builds (-DAMM_BOUNDS_CHECK, tools/build_debug.py) verify that every global load of input
+// Debug builds (-DAMM_BOUNDS_CHECK, argminmax_b200/_build.py:build_boundscheck) verify that every global load of input
 // data lies inside [base, base + n_bytes); violations are counted in a scratch word and
 // surface as AMM_REC_BOUNDS in the record (compute-sanitizer is not available on the pool).
 struct Bounds {
@@ -91,8 +91,8 @@ constexpr int XCHG_SLOT_WORDS = 16;     // 128 B per (parity, rank) slot: 8 reco
 constexpr int XCHG_MAX_WORLD = 16;      // checksum, tag; 2 parities per buffer
 constexpr uint64_t AMM_REC_PEER_TIMEOUT = 4ull;  // record.flags bit: a peer never showed up
 
-// (key, position) candidates for min, max and first NaN.  Positions are tile ids in
-// the streaming phase and element indices in the exact phase.
+// (key, position) candidates for min, max and first NaN.  Positions are global vector
+// indices in the streaming phase and element indices in the exact phase.
 template <typename Key>
 struct Best {
   Key kmin;

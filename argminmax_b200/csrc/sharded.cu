@@ -76,6 +76,7 @@ extern "C" {
 
 int amm_sharded_destroy(amm_sharded* sh) {
   if (!sh) return AMM_OK;
+  DeviceGuard restore(sh->devices[0]);  // the per-device set_device calls below are undone on exit
   for (int g = 0; g < sh->ngpu; ++g) {
     set_device(sh->devices[g]);
     if (sh->streams[g]) {
@@ -99,11 +100,16 @@ int amm_sharded_create(int ngpu, const int* devices, amm_sharded** out) {
   memset(sh, 0, sizeof(*sh));
   sh->ngpu = ngpu;
   for (int g = 0; g < ngpu; ++g) sh->devices[g] = devices ? devices[g] : g;
+  DeviceGuard restore(sh->devices[0]);
   for (int g = 0; g < ngpu; ++g) {
     int rc = amm_workspace_create(sh->devices[g], &sh->ws[g]);
     if (rc) {
       amm_sharded_destroy(sh);
       return rc;
+    }
+    if (set_device(sh->devices[g]) != AMM_OK) {  // streams / buffers belong to device g
+      amm_sharded_destroy(sh);
+      return AMM_ERR_CUDA;
     }
     cudaError_t e = cudaStreamCreateWithFlags(&sh->streams[g], cudaStreamNonBlocking);
     if (e == cudaSuccess)
@@ -182,6 +188,7 @@ int amm_sharded_workspace(amm_sharded* sh, int g, amm_workspace** ws) {
 int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptrs,
                           const uint64_t* shard_lens, int mode, uint64_t out[2]) {
   if (!sh || !dev_ptrs || !shard_lens || !out) return AMM_ERR_ARG;
+  DeviceGuard restore(sh->devices[0]);
   uint64_t total = 0;
   for (int g = 0; g < sh->ngpu; ++g) total += shard_lens[g];
   if (total == 0) return AMM_ERR_EMPTY;

@@ -218,3 +218,46 @@ def test_pipelined_back_to_back_scans_keep_every_result():
         assert L.amm_workspace_wait(ws.handle, s.cuda_stream, 0, out) == 0
         assert (out[0], out[1]) == expected[-1]
         ws.close()
+
+
+def test_current_device_is_left_untouched():
+    """Every entry point restores the caller's current CUDA device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from argminmax_b200 import DeviceSlice, Workspace
+    torch.cuda.set_device(0)
+    t = torch.arange(100_000, dtype=torch.float32, device="cuda:1")
+    ws = Workspace(1)
+    ds = DeviceSlice.from_torch(t, workspace=ws)
+    assert ds.argminmax() == (0, 99_999)
+    x = torch.zeros(4, device="cuda")      # allocates on the *current* device
+    assert x.device.index == 0
+    import ctypes
+    lib = ctypes.CDLL("libcudart.so.12")
+    cur = ctypes.c_int(-1)
+    lib.cudaGetDevice(ctypes.byref(cur))
+    assert cur.value == 0
+    ws.close()
+
+
+def test_default_stream_with_another_current_device():
+    """stream = NULL means 'default stream of the current device': a call on a workspace of
+    device 0 must not be confused by the caller having made device 1 current (long kernels
+    exercise the stream-query fallback of the result poll)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from argminmax_b200 import DeviceSlice, Workspace
+    rng = np.random.default_rng(13)
+    a = random_array("f32", 60_000_000, rng)
+    ds, _keep = to_device(a)            # lives on cuda:0
+    ds._ws = Workspace(0)
+    exp = oracle.argminmax(a, 0)
+    torch.cuda.set_device(1)
+    try:
+        for _ in range(20):
+            assert ds.argminmax() == exp
+    finally:
+        torch.cuda.set_device(0)
+    ds._ws.close()
