@@ -95,6 +95,7 @@ SIGNATURES = {
                                       ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "amm_variant_count": (_i, []),
     "amm_variant_name": (ctypes.c_char_p, [_i]),
+    "amm_measure_call_latency": (_i, [_i, _vp, _u64, _i, _vp, _vp, _i, ctypes.POINTER(ctypes.c_double)]),
     "amm_workspace_last_launch": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), _u64p]),
 }
 

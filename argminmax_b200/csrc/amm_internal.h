@@ -50,6 +50,8 @@ struct amm_workspace {
   int last_grid, last_threads;
   uint64_t launches;
   amm_host_pipeline* pipe;  // lazily created by amm_host_argminmax
+  void* win_scratch;        // records + bounds of the huge-window path (amm_argminmax_windows)
+  size_t win_scratch_bytes;
   // fused cross-GPU exchange (amm_exchange_*): this rank's buffer, the peer pointer table
   int xworld, xrank;
   uint64_t* xbuf;            // cudaMalloc'ed, 2 parities x world slots x 128 B

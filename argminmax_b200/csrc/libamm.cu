@@ -11,7 +11,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <chrono>
 #include <new>
+#include <vector>
 
 #include "../../include/argminmax_b200.h"
 #include "amm_internal.h"
@@ -353,6 +356,7 @@ int amm_workspace_destroy(amm_workspace* ws) {
   DeviceGuard guard(ws->device);
   host_pipeline_destroy(ws);
   exchange_destroy(ws);
+  if (ws->win_scratch) cudaFree(ws->win_scratch);
   if (ws->partials) cudaFree(ws->partials);
   if (ws->ticket) cudaFree(ws->ticket);
   if (ws->rec_dev) cudaFree(ws->rec_dev);
@@ -546,6 +550,89 @@ int amm_combine_records(const amm_record* records, int count, int mode, uint64_t
 }
 
 /* ---- windowed / segmented form --------------------------------------------------------- */
+// A few HUGE windows (>= 32 MiB each): one streaming scan per window (back to back on the
+// stream, pipelined after the first) writing its 64-byte record to scratch, then one tiny
+// kernel turns the records into (argmin, argmax) pairs.  Keeps every SM busy where the
+// one-CTA-per-window kernel would use only n_windows CTAs.
+__global__ void window_records_to_pairs_kernel(const amm_record* recs, const uint64_t* begins,
+                                               const uint64_t* ends, uint64_t n_windows, int mode,
+                                               uint64_t* out) {
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_windows) return;
+  uint64_t imin, imax;
+  if (begins[w] >= ends[w]) {
+    imin = imax = AMM_NO_INDEX;
+  } else {
+    const amm_record r = recs[w];
+    if (mode == AMM_RETURN_NAN && (r.flags & AMM_REC_HAS_NAN)) {
+      imin = imax = r.nan_idx;
+    } else if (!(r.flags & AMM_REC_HAS_VALUE)) {
+      imin = imax = begins[w];
+    } else {
+      imin = r.min_idx;
+      imax = r.max_idx;
+    }
+  }
+  out[2 * w] = imin;
+  out[2 * w + 1] = imax;
+}
+
+static int windows_huge(int dtype, const void* dev_ptr, uint64_t n, const uint64_t* dev_offsets,
+                        uint64_t window, uint64_t n_windows, int mode, amm_workspace* ws,
+                        cudaStream_t stream, uint64_t* dev_out) {
+  const size_t es = amm_dtype_size(dtype);
+  std::vector<uint64_t> bounds(2 * (size_t)n_windows);  // begins | ends
+  if (dev_offsets) {
+    std::vector<uint64_t> offs((size_t)n_windows + 1);
+    AMM_CUDA(cudaMemcpyAsync(offs.data(), dev_offsets, sizeof(uint64_t) * offs.size(),
+                             cudaMemcpyDeviceToHost, stream));
+    AMM_CUDA(cudaStreamSynchronize(stream));
+    for (uint64_t w = 0; w < n_windows; ++w) {
+      uint64_t e = offs[w + 1] < n ? offs[w + 1] : n;
+      uint64_t b = offs[w] < e ? offs[w] : e;
+      bounds[w] = b;
+      bounds[n_windows + w] = e;
+    }
+  } else {
+    for (uint64_t w = 0; w < n_windows; ++w) {
+      uint64_t b = w * window, e = b + window;
+      e = e < n ? e : n;
+      bounds[w] = b < e ? b : e;
+      bounds[n_windows + w] = e;
+    }
+  }
+  // scratch: records + bounds on the device, grown on demand and kept in the workspace
+  const size_t need = (size_t)n_windows * (sizeof(amm_record) + 2 * sizeof(uint64_t));
+  if (ws->win_scratch_bytes < need) {
+    if (ws->win_scratch) AMM_CUDA(cudaFree(ws->win_scratch));
+    ws->win_scratch = nullptr;
+    ws->win_scratch_bytes = 0;
+    AMM_CUDA(cudaMalloc(&ws->win_scratch, need));
+    ws->win_scratch_bytes = need;
+  }
+  amm_record* recs = (amm_record*)ws->win_scratch;
+  uint64_t* dbounds = (uint64_t*)(recs + n_windows);
+  AMM_CUDA(cudaMemcpyAsync(dbounds, bounds.data(), sizeof(uint64_t) * bounds.size(),
+                           cudaMemcpyHostToDevice, stream));
+  const int saved = ws->pipelined;
+  ws->pipelined = 0;  // the first scan must order after whatever produced the data
+  int rc = AMM_OK;
+  for (uint64_t w = 0; w < n_windows && rc == AMM_OK; ++w) {
+    const uint64_t b = bounds[w], e = bounds[n_windows + w];
+    if (b == e) continue;
+    rc = launch(dtype, (const uint8_t*)dev_ptr + b * es, e - b, mode, b, ws, stream, recs + w);
+    ws->pipelined = 1;  // later scans follow one of ours and read data it did not write
+  }
+  ws->pipelined = saved;
+  if (rc) return rc;
+  window_records_to_pairs_kernel<<<(unsigned)((n_windows + 127) / 128), 128, 0, stream>>>(
+      recs, dbounds, dbounds + n_windows, n_windows, mode, dev_out);
+  AMM_CUDA(cudaGetLastError());
+  ws->launches += 1;
+  // `bounds` (pageable) was handed to cudaMemcpyAsync: it is staged before the call returns
+  return AMM_OK;
+}
+
 static int windows_common(int dtype, const void* dev_ptr, uint64_t n, const uint64_t* dev_offsets,
                           uint64_t window, uint64_t n_windows, int mode, amm_workspace* ws,
                           void* stream, uint64_t* dev_out) {
@@ -567,7 +654,20 @@ static int windows_common(int dtype, const void* dev_ptr, uint64_t n, const uint
   p.n_windows = n_windows;
   p.out = dev_out;
   p.mode = mode;
-  return windows_slot(slot, ws, p, n / n_windows, (cudaStream_t)stream);
+  const uint64_t mean = n / n_windows;
+  // Few, large windows: the one-CTA-per-window kernel keeps only n_windows CTAs busy (~40 GB/s
+  // each, ~180 CTAs saturate HBM); a streaming scan per window costs max(~6 us, bytes / HBM rate)
+  // but uses the whole GPU.  Pick whichever the model says is faster.
+  const double total_bytes = (double)n * (double)amm_dtype_size(dtype);
+  const double win_bytes = total_bytes / (double)n_windows;
+  const double busy_ctas = n_windows < 180 ? (double)n_windows : 180.0;
+  const double t_cta_us = total_bytes / (busy_ctas * 40.0e3);
+  const double per_scan_us = win_bytes / 7.0e6 > 6.0 ? win_bytes / 7.0e6 : 6.0;
+  const double t_scan_us = (double)n_windows * per_scan_us;
+  if (n_windows <= 65536 && win_bytes >= (double)(1 << 20) && t_scan_us < t_cta_us)
+    return windows_huge(dtype, dev_ptr, n, dev_offsets, window, n_windows, mode, ws,
+                        (cudaStream_t)stream, dev_out);
+  return windows_slot(slot, ws, p, mean, (cudaStream_t)stream);
 }
 
 int amm_argminmax_windows(int dtype, const void* dev_ptr, uint64_t n, const uint64_t* dev_offsets,
@@ -625,6 +725,32 @@ int amm_copy_to_host(int device, void* dst_host, const void* src_dev, size_t byt
   int rc = AMM_OK;
   (void)rc;
   AMM_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+  return AMM_OK;
+}
+
+/* Host wall-clock latency of the synchronous call, measured inside the library so that no
+   binding overhead (ctypes, JNI, ...) is included: `calls` timed amm_argminmax calls after
+   calls/10 + 10 warm-up calls; reports median / min / p99 in microseconds. */
+int amm_measure_call_latency(int dtype, const void* dev_ptr, uint64_t n, int mode,
+                             amm_workspace* ws, void* stream, int calls, double out_us[3]) {
+  if (!out_us || calls < 1) return AMM_ERR_ARG;
+  uint64_t r[2];
+  for (int i = 0; i < calls / 10 + 10; ++i) {
+    int rc = amm_argminmax(dtype, dev_ptr, n, mode, ws, stream, r);
+    if (rc) return rc;
+  }
+  std::vector<double> us((size_t)calls);
+  for (int i = 0; i < calls; ++i) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = amm_argminmax(dtype, dev_ptr, n, mode, ws, stream, r);
+    const auto t1 = std::chrono::steady_clock::now();
+    if (rc) return rc;
+    us[(size_t)i] = std::chrono::duration<double, std::micro>(t1 - t0).count();
+  }
+  std::sort(us.begin(), us.end());
+  out_us[0] = us[us.size() / 2];
+  out_us[1] = us[0];
+  out_us[2] = us[us.size() * 99 / 100];
   return AMM_OK;
 }
 

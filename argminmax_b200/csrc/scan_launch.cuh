@@ -1,6 +1,7 @@
 // scan_launch.cuh -- host-side launch geometry for the scan kernels (included by the
 // per-policy-group translation units, scan_inst.cu).
 #pragma once
+#include <stdlib.h>
 #include <string.h>
 
 #include "amm_internal.h"
@@ -139,20 +140,32 @@ static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cuda
   }
 }
 
-// Windowed form: warp per window for short windows, CTA per window for long ones.
+// Windowed form.  Regimes (B200 measurements, tools/windows_bench.py):
+//   <= 2 KB per window            8 lanes per window (4 windows per warp)
+//   >= 4096 windows               one warp per window (enough warps to fill the machine)
+//   >= 4 x SMs windows            one 256-thread CTA per window, 16 KB in flight per CTA
+//   fewer                         one 512-thread CTA per window, 64 KB in flight per CTA
+//                                 (or one streaming scan per window, see windows_huge)
 template <class P>
 static int launch_windows(amm_workspace* ws, const WindowParams& p, uint64_t mean_window,
                           cudaStream_t stream) {
   const uint64_t cap = (uint64_t)ws->sm_count * 8;
-  if (mean_window <= 32768) {
-    uint64_t grid = (p.n_windows + 7) / 8;  // 8 warps per CTA
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
-    argminmax_windows_warp_kernel<P><<<(unsigned)grid, 256, 0, stream>>>(p);
+  uint64_t grid;
+  if (mean_window * sizeof(typename P::Elem) <= 2048) {
+    grid = (p.n_windows + 31) / 32;
+    grid = grid > cap ? cap : (grid < 1 ? 1 : grid);
+    argminmax_windows_warp_kernel<P, 8><<<(unsigned)grid, 256, 0, stream>>>(p);
+  } else if (p.n_windows >= 4096) {
+    grid = (p.n_windows + 7) / 8;  // 8 warps per CTA, one window per warp
+    grid = grid > cap ? cap : (grid < 1 ? 1 : grid);
+    argminmax_windows_warp_kernel<P, 32><<<(unsigned)grid, 256, 0, stream>>>(p);
+  } else if (p.n_windows >= (uint64_t)ws->sm_count * 4) {
+    grid = p.n_windows < cap ? p.n_windows : cap;
+    argminmax_windows_cta_kernel<P, 256, 4><<<(unsigned)grid, 256, 0, stream>>>(p);
   } else {
-    uint64_t grid = p.n_windows < cap ? p.n_windows : cap;
-    if (grid < 1) grid = 1;
-    argminmax_windows_cta_kernel<P><<<(unsigned)grid, 256, 0, stream>>>(p);
+    grid = p.n_windows < cap ? p.n_windows : cap;
+    grid = grid < 1 ? 1 : grid;
+    argminmax_windows_cta_kernel<P, 512, 8><<<(unsigned)grid, 512, 0, stream>>>(p);
   }
   AMM_CUDA(cudaGetLastError());
   ws->launches += 1;

@@ -81,7 +81,7 @@ struct WindowGeom {
 };
 
 // value-only fold of this thread's share of the window; units are visited in ascending order
-template <class P, int STRIDE>
+template <class P, int STRIDE, int UN = 4>
 __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeom<P>& g,
                                             uint32_t t, Best<typename P::Key>& x) {
   using Elem = typename P::Elem;
@@ -98,14 +98,13 @@ __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeo
     }
     if (has_nan && x.pnan == POS_NONE) x.pnan = unit;
   };
-  if (t < g.hc) {  // unit 0: one head element per thread
+  for (uint32_t h = t; h < g.hc; h += STRIDE) {  // unit 0: the head, one element at a time
     Key k;
     bool valid, is_nan;
-    P::classify(e[g.begin + t], k, valid, is_nan);
+    P::classify(e[g.begin + h], k, valid, is_nan);
     consider(k, k, valid, P::TRACK_NAN && is_nan, 0);
   }
   const uint8_t* vbase = base + g.a0 * sizeof(Elem);
-  constexpr int UN = 4;
   for (uint64_t v0 = t; v0 < g.nv; v0 += (uint64_t)UN * STRIDE) {
     uint32_t w[UN][4];
 #pragma unroll
@@ -128,41 +127,50 @@ __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeo
       }
     }
   }
-  if (t < g.tc) {  // unit nv+1: one tail element per thread
+  for (uint32_t q = t; q < g.tc; q += STRIDE) {  // unit nv+1: the tail
     Key k;
     bool valid, is_nan;
-    P::classify(e[g.a0 + g.nv * WindowGeom<P>::VE + t], k, valid, is_nan);
+    P::classify(e[g.a0 + g.nv * WindowGeom<P>::VE + q], k, valid, is_nan);
     consider(k, k, valid, P::TRACK_NAN && is_nan, g.nv + 1);
   }
 }
 
-// One warp re-reads the winning units (one element per lane) and writes the window's answer.
-template <class P>
-__device__ __forceinline__ void window_locate_store(const WindowParams& p, uint64_t w,
+// A group of G lanes (G = 32: the whole warp; G = 8: four windows per warp, for windows of a few
+// hundred bytes) re-reads the winning units, G elements per step, and a ballot picks the first
+// match; lane 0 of the group writes the window's answer.  Every lane of the warp executes
+// the same ballots (inactive groups contribute no hits).
+template <class P, int G>
+__device__ __forceinline__ void window_locate_store(const WindowParams& p, uint64_t w, bool active,
                                                     const WindowGeom<P>& g,
                                                     const Best<typename P::Key>& x, uint32_t lane) {
   using Elem = typename P::Elem;
   using Key = typename P::Key;
   const Elem* e = reinterpret_cast<const Elem*>(p.base);
+  const uint32_t sl = lane % G, shift = (lane / G) * G;
+  const uint32_t gmask = (G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u);
   uint64_t res[3] = {POS_NONE, POS_NONE, POS_NONE};  // min, max, first NaN
   const uint64_t units[3] = {x.pmin, x.pmax, x.pnan};
 #pragma unroll
   for (int c = 0; c < (P::TRACK_NAN ? 3 : 2); ++c) {
-    if (units[c] == POS_NONE) continue;  // warp-uniform
-    uint64_t first;
-    uint32_t count;
-    g.unit_range(units[c], first, count);
-    bool hit = false;
-    if (lane < count) {
-      Key k;
-      bool valid, is_nan;
-      P::classify(e[first + lane], k, valid, is_nan);
-      hit = (c == 0) ? (valid && k == x.kmin) : (c == 1) ? (valid && k == x.kmax) : is_nan;
+    uint64_t first = 0;
+    uint32_t count = 0;
+    if (active && units[c] != POS_NONE) g.unit_range(units[c], first, count);
+    constexpr uint32_t STEPS = (WindowGeom<P>::VE + G - 1) / G;  // units hold <= VE elements
+#pragma unroll
+    for (uint32_t st = 0; st < STEPS; ++st) {
+      const uint32_t k_in_unit = st * G + sl;
+      bool hit = false;
+      if (k_in_unit < count) {
+        Key k;
+        bool valid, is_nan;
+        P::classify(e[first + k_in_unit], k, valid, is_nan);
+        hit = (c == 0) ? (valid && k == x.kmin) : (c == 1) ? (valid && k == x.kmax) : is_nan;
+      }
+      const uint32_t m = (__ballot_sync(0xFFFFFFFFu, hit) >> shift) & gmask;
+      if (m != 0 && res[c] == POS_NONE) res[c] = first + st * G + (uint64_t)(__ffs(m) - 1);
     }
-    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-    if (m) res[c] = first + (uint64_t)(__ffs(m) - 1);
   }
-  if (lane == 0) {
+  if (active && sl == 0) {
     uint64_t imin, imax;
     if (g.begin == g.end) {
       imin = imax = AMM_NO_INDEX;
@@ -179,16 +187,16 @@ __device__ __forceinline__ void window_locate_store(const WindowParams& p, uint6
   }
 }
 
-// Warp all-reduce of the (key, unit) candidates with 32-bit unit ids (a window has fewer than
-// 2^32 units) and without the NaN field for policies that do not track NaNs: per-window cost
-// matters when windows are a few hundred elements.
-template <class P>
-__device__ __forceinline__ void window_warp_reduce(Best<typename P::Key>& x) {
+// All-reduce of the (key, unit) candidates inside a group of G lanes, with 32-bit unit ids (a
+// window has fewer than 2^32 units) and without the NaN field for policies that do not track
+// NaNs: per-window cost matters when windows are a few hundred elements.
+template <class P, int G>
+__device__ __forceinline__ void window_group_reduce(Best<typename P::Key>& x) {
   using Key = typename P::Key;
   Key kmin = x.kmin, kmax = x.kmax;
   uint32_t umin = (uint32_t)x.pmin, umax = (uint32_t)x.pmax, unan = (uint32_t)x.pnan;  // NONE -> ~0u
 #pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
+  for (int m = G / 2; m >= 1; m >>= 1) {
     const Key okmin = __shfl_xor_sync(0xFFFFFFFFu, kmin, m);
     const Key okmax = __shfl_xor_sync(0xFFFFFFFFu, kmax, m);
     const uint32_t oumin = __shfl_xor_sync(0xFFFFFFFFu, umin, m);
@@ -213,28 +221,32 @@ __device__ __forceinline__ void window_warp_reduce(Best<typename P::Key>& x) {
   x.pnan = (!P::TRACK_NAN || unan == 0xFFFFFFFFu) ? POS_NONE : (uint64_t)unan;
 }
 
-// one warp per window, grid-stride over windows
-template <class P>
+// one group of G lanes per window (32 / G windows per warp), grid-stride over windows
+template <class P, int G>
 __global__ void __launch_bounds__(256) argminmax_windows_warp_kernel(const WindowParams p) {
   using Key = typename P::Key;
+  constexpr uint32_t PER_WARP = 32 / G;
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
-  for (uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < p.n_windows;
-       w += warps) {
-    uint64_t begin, end;
-    window_bounds<P>(p, w, begin, end);
+  const uint64_t n_rounds = (p.n_windows + PER_WARP - 1) / PER_WARP;
+  for (uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rounds;
+       r += warps) {
+    const uint64_t w = r * PER_WARP + lane / G;
+    const bool active = w < p.n_windows;
+    uint64_t begin = 0, end = 0;
+    if (active) window_bounds<P>(p, w, begin, end);
     const WindowGeom<P> g(p.base, begin, end);
     Best<Key> x;
     x.clear();
-    window_fold<P, 32>(p.base, g, lane, x);
-    window_warp_reduce<P>(x);
-    window_locate_store<P>(p, w, g, x, lane);
+    window_fold<P, G>(p.base, g, lane % G, x);
+    window_group_reduce<P, G>(x);
+    window_locate_store<P, G>(p, w, active, g, x, lane);
   }
 }
 
 // one CTA per window (large windows)
-template <class P>
-__global__ void __launch_bounds__(256) argminmax_windows_cta_kernel(const WindowParams p) {
+template <class P, int THREADS, int UN>
+__global__ void __launch_bounds__(THREADS) argminmax_windows_cta_kernel(const WindowParams p) {
   using Key = typename P::Key;
   __shared__ Best<Key> smem[32];
   for (uint64_t w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
@@ -243,9 +255,9 @@ __global__ void __launch_bounds__(256) argminmax_windows_cta_kernel(const Window
     const WindowGeom<P> g(p.base, begin, end);
     Best<Key> x;
     x.clear();
-    window_fold<P, 256>(p.base, g, threadIdx.x, x);
+    window_fold<P, THREADS, UN>(p.base, g, threadIdx.x, x);  // THREADS * UN * 16 B in flight
     x = block_reduce(x, smem);
-    if (threadIdx.x < 32) window_locate_store<P>(p, w, g, x, threadIdx.x);
+    if (threadIdx.x < 32) window_locate_store<P, 32>(p, w, true, g, x, threadIdx.x);
   }
 }
 

@@ -333,17 +333,24 @@ def main() -> int:
                         "consecutive steps pipelined (PDL), which hides each kernel's fold/publish tail",
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)}
 
-    # ---- small-n latency: us per call at 1M elements through the synchronous C-ABI call
+    # ---- small-n latency: us per call at 1M elements, synchronous C-ABI call timed inside the
+    #      library (amm_measure_call_latency: host wall clock, no Python in the loop)
+    import ctypes
+    lat3 = (ctypes.c_double * 3)()
+    rc = amm.lib().amm_measure_call_latency(amm.DTYPES[DTYPE], data.data_ptr(), 1 << 20, amm.IGNORE_NAN,
+                                            ws.handle, stream, 2000, lat3)
+    if rc:
+        raise RuntimeError(f"amm_measure_call_latency rc={rc}")
+    us_1m = lat3[0]
     small = amm.DeviceSlice.from_torch(data[: 1 << 20], dtype=DTYPE, workspace=ws, stream=stream)
     for _ in range(20):
         small.argminmax()
-    torch.cuda.synchronize()
     lat = []
     for _ in range(300):
         t0 = time.perf_counter()
         small.argminmax()
         lat.append((time.perf_counter() - t0) * 1e6)
-    us_1m = statistics.median(lat)
+    us_1m_python = statistics.median(lat)
 
     # ---- e2e: the public host-slice call on pinned HOST input (H2D inside the timed region)
     e2e = None
@@ -354,8 +361,6 @@ def main() -> int:
         torch.cuda.synchronize()
         hs = amm.HostSlice.from_torch(host, dtype=DTYPE, device=local_rank, workspace=ws)
         rec = amm.AmmRecord()
-        import ctypes
-
         def e2e_step():
             rc = amm.lib().amm_host_argminmax_record(amm.DTYPES[DTYPE], hs.host_ptr, hs.n, amm.IGNORE_NAN,
                                                      rank * n, ws.handle, ctypes.byref(rec))
@@ -416,6 +421,9 @@ def main() -> int:
             "elements_per_s": round(world * n / (ms_per_step / 1e3), 1),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "us_per_call_1m": round(us_1m, 2),
+            "us_per_call_1m_detail": {"median": round(lat3[0], 2), "min": round(lat3[1], 2), "p99": round(lat3[2], 2),
+                                      "through_python_ctypes_median": round(us_1m_python, 2),
+                                      "what": "f32 n=2^20, synchronous amm_argminmax, host wall clock"},
             "result": list(result), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -282,6 +282,10 @@ int amm_workspace_get_tuning(const amm_workspace* ws, int* threads, int* ctas_pe
                              int* sm_count);
 int amm_variant_count(void);
 const char* amm_variant_name(int variant);
+/* Host wall-clock latency of the synchronous amm_argminmax call, measured inside the library
+   (no binding overhead): out_us = {median, min, p99} microseconds over `calls` calls. */
+int amm_measure_call_latency(int dtype, const void* dev_ptr, uint64_t n, int mode,
+                             amm_workspace* ws, void* stream, int calls, double out_us[3]);
 /* grid size and kernels launched by the most recent amm_argminmax_launch on ws */
 int amm_workspace_last_launch(const amm_workspace* ws, int* grid, int* threads, uint64_t* launches_total);
 

@@ -58,3 +58,29 @@ def test_ragged_windows_with_empty_and_duplicates(dt):
     for mode in modes_for(dt):
         got = [tuple(r) for r in ds.argminmax_windows(offs, mode).cpu().tolist()]
         assert got == _expected(a, bounds, mode)
+
+
+def test_huge_windows_take_the_streaming_path():
+    """Few windows of >= 32 MiB each: one pipelined streaming scan per window + a conversion
+    kernel (windows_huge in libamm.cu); answers as for any other window size."""
+    import torch
+    rng = np.random.default_rng(5)
+    n = 35_000_003
+    a = random_array("f32", n, rng)
+    a[rng.integers(0, n, 50)] = np.nan
+    ds, _keep = to_device(a)
+    window = 10_000_000
+    bounds = [(w * window, min(n, (w + 1) * window)) for w in range(-(-n // window))]
+    for mode in (0, 1):
+        got = [tuple(r) for r in ds.argminmax_windows(window, mode).cpu().tolist()]
+        assert got == _expected(a, bounds, mode)
+    cuts = np.array([0, 9_000_001, 9_000_001, 20_000_000, n], dtype=np.int64)   # one empty window
+    offs = torch.from_numpy(cuts).cuda()
+    bounds = list(zip(cuts[:-1].tolist(), cuts[1:].tolist()))
+    got = [tuple(r) for r in ds.argminmax_windows(offs, 0).cpu().tolist()]
+    assert got == _expected(a, bounds, 0)
+    b = random_array("u8", 150_000_000, rng)
+    db, _kb = to_device(b)
+    w8 = 50_000_000
+    got = [tuple(r) for r in db.argminmax_windows(w8, 0).cpu().tolist()]
+    assert got == _expected(b, [(0, w8), (w8, 2 * w8), (2 * w8, 3 * w8)], 0)
