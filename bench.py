@@ -61,7 +61,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []  # (t, sm_mhz, reasons_mask)
+        self.samples = []  # (t, sm_mhz, reasons_mask, mem_mhz, watts)
         self.stop_flag = False
         self.ok = False
         try:
@@ -85,7 +85,12 @@ class ClockSampler(threading.Thread):
                     reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:  # noqa: BLE001
                     reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                self.samples.append((time.perf_counter(), mhz, reasons))
+                try:
+                    mem = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_MEM)
+                    watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:  # noqa: BLE001
+                    mem, watts = None, None
+                self.samples.append((time.perf_counter(), mhz, reasons, mem, watts))
             except Exception:  # noqa: BLE001
                 pass
             time.sleep(0.002)
@@ -105,8 +110,12 @@ class ClockSampler(threading.Thread):
         mask = 0
         for s in inside:
             mask |= s[2]
+        mems = [s[3] for s in inside if s[3] is not None]
+        watts = [s[4] for s in inside if s[4] is not None]
         return {"sm_mhz": statistics.median(s[1] for s in inside), "sm_max_mhz": self.max_mhz,
-                "reasons": [k for k, bit in names.items() if mask & bit], "samples": len(inside)}
+                "reasons": [k for k, bit in names.items() if mask & bit], "samples": len(inside),
+                "mem_mhz": statistics.median(mems) if mems else None,
+                "power_w_max": round(max(watts), 1) if watts else None}
 
 
 # ------------------------------------------------------------------------ data
@@ -310,6 +319,7 @@ def main() -> int:
     value = world * nbytes / ms_per_step / 1e6  # GB/s, aggregate
     clocks = sampler.summary(t_wall0, t_wall1)
     main_launch = ws.last_launch()
+    tuning = ws.get_tuning()  # geometry of the timed scans (later probes use other shapes)
 
     # ---- kernel-only duration of the dominant kernel (roofline), this rank, same stream,
     #      launches strictly serialised (no overlap between consecutive kernels)
@@ -399,7 +409,6 @@ def main() -> int:
         cpu = cpu_baseline(np.ascontiguousarray(sample), budget_s=12.0)
 
     sampler.stop_flag = True
-    tuning = ws.get_tuning()
     ll = main_launch
     if rank == 0:
         line = {
