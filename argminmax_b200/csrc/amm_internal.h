@@ -50,6 +50,8 @@ struct amm_workspace {
   int last_grid, last_threads;
   uint64_t launches;
   amm_host_pipeline* pipe;  // lazily created by amm_host_argminmax
+  int win_staged;           // short windows take the TMA-staged kernel (AMM_WIN_STAGED=0: old path)
+  int win_lane_bytes;       // ... with one lane per this many bytes of window (1..8 lanes)
   void* win_scratch;        // records + bounds of the huge-window path (amm_argminmax_windows)
   size_t win_scratch_bytes;
   // fused cross-GPU exchange (amm_exchange_*): this rank's buffer, the peer pointer table

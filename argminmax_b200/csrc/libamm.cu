@@ -314,6 +314,9 @@ static int workspace_init(amm_workspace* ws, int device) {
   if (ws->direct_ctas_per_sm < 1 || ws->direct_ctas_per_sm > 32) ws->direct_ctas_per_sm = 2;
   ws->publish_fence = getenv("AMM_PUBLISH_FENCE") ? atoi(getenv("AMM_PUBLISH_FENCE")) : 0;
   ws->pdl = getenv("AMM_PDL") ? atoi(getenv("AMM_PDL")) : 1;
+  ws->win_staged = getenv("AMM_WIN_STAGED") ? atoi(getenv("AMM_WIN_STAGED")) : 1;
+  ws->win_lane_bytes = getenv("AMM_WIN_LANE_BYTES") ? atoi(getenv("AMM_WIN_LANE_BYTES")) : 128;
+  if (ws->win_lane_bytes < 16 || ws->win_lane_bytes > 1024) ws->win_lane_bytes = 128;
   ws->max_grid = ws->sm_count * 32;
   // partials sized for the widest Best<int64_t> (40 B) -> 64 B slots
   AMM_CUDA(cudaMalloc(&ws->partials, (size_t)ws->max_grid * 64));

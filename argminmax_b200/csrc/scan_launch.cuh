@@ -141,16 +141,48 @@ static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cuda
 }
 
 // Windowed form.  Regimes (B200 measurements, tools/windows_bench.py):
-//   <= 2 KB per window            8 lanes per window (4 windows per warp)
+//   <= 1 KB per window            TMA-staged blocks of windows, 1/2/4/8 lanes per window
+//   <= 2 KB per window            8 lanes per window (4 windows per warp), loads from global
 //   >= 4096 windows               one warp per window (enough warps to fill the machine)
 //   >= 4 x SMs windows            one 256-thread CTA per window, 16 KB in flight per CTA
 //   fewer                         one 512-thread CTA per window, 64 KB in flight per CTA
 //                                 (or one streaming scan per window, see windows_huge)
+template <class P, int L>
+static int launch_windows_staged(amm_workspace* ws, const WindowParams& p, uint64_t mean_bytes,
+                                 cudaStream_t stream) {
+  constexpr int THREADS = 128;
+  constexpr uint64_t WPB = THREADS / L;
+  // stage = the bytes of one block of windows (+ alignment slack); ragged windows get 2x the
+  // mean (what does not fit is read from global memory by the kernel)
+  const uint64_t fixed_bytes = (p.window < p.n ? p.window : p.n) * sizeof(typename P::Elem);
+  uint64_t stage = (p.offsets ? 2 * mean_bytes : fixed_bytes) * WPB + 64;
+  stage = (stage + 127) / 128 * 128;
+  if (stage < 1024) stage = 1024;
+  if (stage > 20480) stage = 20480;  // 2 stages + static smem stay below the 48 KB default limit
+  const uint64_t n_blocks = (p.n_windows + WPB - 1) / WPB;
+  uint64_t grid = (uint64_t)ws->sm_count * 6;
+  grid = n_blocks < grid ? n_blocks : grid;
+  grid = grid < 1 ? 1 : grid;
+  argminmax_windows_staged_kernel<P, L, THREADS>
+      <<<(unsigned)grid, THREADS, (size_t)(2 * stage), stream>>>(p, (uint32_t)stage);
+  AMM_CUDA(cudaGetLastError());
+  ws->launches += 1;
+  return AMM_OK;
+}
+
 template <class P>
 static int launch_windows(amm_workspace* ws, const WindowParams& p, uint64_t mean_window,
                           cudaStream_t stream) {
   const uint64_t cap = (uint64_t)ws->sm_count * 8;
   uint64_t grid;
+  const uint64_t mean_bytes = mean_window * sizeof(typename P::Elem);
+  const uint64_t lane_bytes = (uint64_t)ws->win_lane_bytes;  // target bytes per lane
+  if (mean_bytes <= 8 * lane_bytes && mean_bytes <= 1024 && ws->win_staged) {
+    if (mean_bytes <= lane_bytes) return launch_windows_staged<P, 1>(ws, p, mean_bytes, stream);
+    if (mean_bytes <= 2 * lane_bytes) return launch_windows_staged<P, 2>(ws, p, mean_bytes, stream);
+    if (mean_bytes <= 4 * lane_bytes) return launch_windows_staged<P, 4>(ws, p, mean_bytes, stream);
+    return launch_windows_staged<P, 8>(ws, p, mean_bytes, stream);
+  }
   if (mean_window * sizeof(typename P::Elem) <= 2048) {
     grid = (p.n_windows + 31) / 32;
     grid = grid > cap ? cap : (grid < 1 ? 1 : grid);

@@ -244,6 +244,356 @@ __global__ void __launch_bounds__(256) argminmax_windows_warp_kernel(const Windo
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// SHORT windows (<= 1 KiB each: the down-sampling case with many small bins).  Per-window
+// overhead dominates there, and a warp that reads 32 different windows straight from global
+// memory touches 32 different cache lines per load instruction.  So:
+//   * the CTA processes BLOCKS of consecutive windows; the bytes of a whole block are one
+//     contiguous range of the array and are fetched by ONE TMA bulk copy (cp.async.bulk,
+//     global -> shared, completion on an mbarrier) issued by thread 0 -- no per-thread load
+//     instructions, no address arithmetic, and the copy of block k+1 runs while block k is
+//     being folded (two stages);
+//   * L = 1, 2, 4 or 8 lanes share a window and read it from shared memory with 128-bit loads
+//     (the start vector is rotated per window so that lanes of one quarter-warp hit different
+//     banks even when the window size is a multiple of 128 bytes);
+//   * same value-only fold per 16-byte unit as everywhere else, lexicographic (key, unit)
+//     bookkeeping (units are visited in rotated order), a shuffle reduce inside the lane
+//     group, and the winning units are resolved in registers by up to three lanes in parallel.
+// Anything the stage does not hold -- the <= 15 bytes before the first / after the last 16-byte
+// aligned address of the array, windows beyond the stage capacity when windows are ragged, or
+// windows given in non-ascending order -- is read from global memory through the same generic
+// loads, so the kernel is correct for every input the other window kernels accept.
+// ---------------------------------------------------------------------------------------
+// Where one lane finds the data of ITS window.  The aligned 16-byte vectors of the window
+// (units 1..nv) are either all inside the stage -- then they are read with 32-bit shared-memory
+// addresses -- or they are read from global memory; the decision is made once per window.
+// Single elements (unaligned head / tail, a few per window at most) check the staged range
+// per access.
+struct WinSrc {
+  const uint8_t* base;   // global: element 0 of the array
+  uint64_t a0, a1;       // staged byte range relative to `base`
+  uint32_t stage_s;      // shared-memory address of the staged byte a0
+  bool vec_staged;       // units 1..nv of this lane's window are inside [a0, a1)
+  uint32_t vec_s;        // shared-memory address of unit 1   (vec_staged)
+  const uint8_t* vec_g;  // global address of unit 1
+  template <class Elem>
+  __device__ __forceinline__ Elem elem(uint64_t i) const {
+    const uint64_t q = i * sizeof(Elem);
+    if (q >= a0 && q + sizeof(Elem) <= a1) {
+      const uint32_t addr = stage_s + (uint32_t)(q - a0);
+      uint32_t v;
+      if (sizeof(Elem) == 1) {
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+        return (Elem)v;
+      } else if (sizeof(Elem) == 2) {
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+        return (Elem)v;
+      } else if (sizeof(Elem) == 4) {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+        return (Elem)v;
+      } else {
+        unsigned long long v8;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v8) : "r"(addr));
+        return (Elem)v8;
+      }
+    }
+    return *reinterpret_cast<const Elem*>(base + q);
+  }
+  template <bool STAGED>
+  __device__ __forceinline__ void vec(uint32_t v, uint32_t (&w)[4]) const {
+    if (STAGED) {
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                   : "r"(vec_s + v * 16u));
+    } else {
+      VecLoad<16>::ld(vec_g + (uint64_t)v * 16, w);
+    }
+  }
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) {
+  return (uint32_t)__cvta_generic_to_shared(ptr);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "AMM_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra AMM_MBAR_DONE;\n"
+      "bra AMM_MBAR_WAIT;\n"
+      "AMM_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// TMA bulk copy global -> shared (SASS UBLKCP); src, dst 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Running (key, unit) candidates of one lane; units are 32-bit (a window handled here has far
+// fewer than 2^32 units), 0xFFFFFFFF = none yet.
+template <typename Key>
+struct WinBest {
+  Key kmin, kmax;
+  uint32_t umin, umax, unan;
+  __device__ __forceinline__ void clear() {
+    kmin = KeyLim<Key>::MAXV;
+    kmax = KeyLim<Key>::MINV;
+    umin = umax = unan = 0xFFFFFFFFu;
+  }
+  // full lexicographic rule (units may arrive in any order)
+  template <bool TRACK_NAN>
+  __device__ __forceinline__ void consider(Key k0, Key k1, bool valid, bool has_nan, uint32_t unit) {
+    if (valid && (k0 < kmin || (k0 == kmin && unit < umin))) {
+      kmin = k0;
+      umin = unit;
+    }
+    if (valid && (k1 > kmax || (k1 == kmax && unit < umax))) {
+      kmax = k1;
+      umax = unit;
+    }
+    if (TRACK_NAN && has_nan && unit < unan) unan = unit;
+  }
+};
+
+// value-only fold of this lane's vectors l, l+L, l+2L, ... (units v+1), started at a per-window
+// rotation so that the lanes of a quarter-warp do not all hit the same shared-memory banks
+template <class P, int L, bool STAGED>
+__device__ __forceinline__ void staged_fold_vectors(const WinSrc& src, uint32_t nv, uint32_t l,
+                                                    uint32_t wi, WinBest<typename P::Key>& x) {
+  using Key = typename P::Key;
+  const uint32_t cnt = nv > l ? (nv - l + L - 1) / L : 0;
+  if (cnt == 0) return;
+  uint32_t kk = STAGED ? wi % cnt : 0;  // rotation only matters for shared-memory banks
+  constexpr int UN = 4;
+  for (uint32_t k0 = 0; k0 < cnt; k0 += UN) {
+    uint32_t wv[UN][4];
+    uint32_t vv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      vv[u] = l + kk * L;
+      if (k0 + u < cnt) src.vec<STAGED>(vv[u], wv[u]);
+      ++kk;
+      kk = kk >= cnt ? 0 : kk;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (k0 + u < cnt) {
+        typename P::Acc acc;
+        P::init(acc, &wv[u][0]);
+#pragma unroll
+        for (int q = P::WPI; q < 4; q += P::WPI) P::feed(acc, &wv[u][q]);
+        Key a, b;
+        bool valid, has_nan;
+        P::finish(acc, a, b, valid, has_nan);
+        x.template consider<P::TRACK_NAN>(a, b, valid, has_nan, vv[u] + 1);
+      }
+    }
+  }
+}
+
+// first element of unit `u` of window `g` that matches candidate `c` (0: key == kmin, 1: key ==
+// kmax, 2: NaN), or POS_NONE.  One thread, in registers for the 16-byte units.
+template <class P>
+__device__ __forceinline__ uint64_t staged_locate(const WinSrc& src, const WindowGeom<P>& g,
+                                                  uint32_t unit, int c, typename P::Key want) {
+  using Elem = typename P::Elem;
+  using Key = typename P::Key;
+  constexpr int VE = (int)WindowGeom<P>::VE;
+  auto is_hit = [&](Elem raw) {
+    Key k;
+    bool valid, is_nan;
+    P::classify(raw, k, valid, is_nan);
+    return c == 2 ? is_nan : (valid && k == want);
+  };
+  uint64_t first;
+  uint32_t count;
+  g.unit_range(unit, first, count);
+  int found = -1;
+  if (unit >= 1 && unit <= g.nv) {
+    uint32_t w[4];
+    if (src.vec_staged) {
+      src.vec<true>(unit - 1, w);
+    } else {
+      src.vec<false>(unit - 1, w);
+    }
+#pragma unroll
+    for (int e = VE - 1; e >= 0; --e) found = is_hit(vec_elem<P, 4>(w, e)) ? e : found;
+  } else {
+    for (int e = (int)count - 1; e >= 0; --e) found = is_hit(src.elem<Elem>(first + e)) ? e : found;
+  }
+  return found < 0 ? POS_NONE : first + (uint64_t)found;
+}
+
+template <class P, int L, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    argminmax_windows_staged_kernel(const WindowParams p, const uint32_t stage_bytes) {
+  using Elem = typename P::Elem;
+  using Key = typename P::Key;
+  constexpr uint32_t WPB = THREADS / L;  // windows per block
+  extern __shared__ __align__(128) uint8_t dsm[];  // 2 stages x stage_bytes
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ uint64_t s_range[2][2];  // staged byte range [a0, a1) of each stage
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  const uint32_t wi = tid / L, l = tid % L;  // window in block, lane in window
+  const uint64_t n_blocks = (p.n_windows + WPB - 1) / WPB;
+  const bool out16 = (((uint64_t)(uintptr_t)p.out) & 15) == 0;
+
+  // thread 0: staged byte range of block `blk`, published in s_range[s], and the copy itself
+  auto issue = [&](uint64_t blk, uint32_t s) {
+    const uint64_t abase = (uint64_t)(uintptr_t)p.base;
+    const uint64_t n_bytes = p.n * sizeof(Elem);
+    // 16-byte aligned interior of the array, as byte offsets relative to base
+    const uint64_t in_lo = (16 - (abase & 15)) & 15;
+    const uint64_t hi_abs = (abase + n_bytes) & ~(uint64_t)15;
+    const uint64_t in_hi = hi_abs > abase ? hi_abs - abase : 0;  // may be < in_lo (tiny arrays)
+    const uint64_t wb = blk * WPB;
+    const uint64_t we = (wb + WPB < p.n_windows ? wb + WPB : p.n_windows) - 1;  // last window
+    uint64_t b0, e0, b1, e1;
+    window_bounds<P>(p, wb, b0, e0);
+    window_bounds<P>(p, we, b1, e1);
+    uint64_t lo = b0 * sizeof(Elem), hi = e1 * sizeof(Elem);
+    if (hi < lo) hi = lo;  // offsets not ascending: such windows are read from global memory
+    lo = (lo + abase) & ~(uint64_t)15;  // floor to a 16-byte boundary (absolute address) ...
+    lo = lo > abase ? lo - abase : 0;   // ... back to an offset, never before in_lo
+    lo = lo < in_lo ? in_lo : lo;
+    hi = ((hi + abase + 15) & ~(uint64_t)15) - abase;
+    hi = hi > in_hi ? in_hi : hi;
+    if (hi > lo + stage_bytes) hi = lo + stage_bytes;
+    if (hi < lo) hi = lo;
+    s_range[s][0] = lo;
+    s_range[s][1] = hi;
+    const uint32_t bytes = (uint32_t)(hi - lo);
+    if (bytes != 0) {
+      mbar_arrive_expect_tx(&s_bar[s], bytes);
+      tma_bulk_g2s(dsm + (size_t)s * stage_bytes, p.base + lo, bytes, &s_bar[s]);
+    } else {
+      mbar_arrive(&s_bar[s]);
+    }
+  };
+
+  uint64_t blk = blockIdx.x;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (blk < n_blocks) issue(blk, 0);
+  }
+  __syncthreads();
+  uint32_t it = 0;
+  for (; blk < n_blocks; blk += gridDim.x, ++it) {
+    const uint32_t s = it & 1;
+    // stage s^1 was released by the barrier that ended the previous iteration
+    if (tid == 0 && blk + gridDim.x < n_blocks) issue(blk + gridDim.x, s ^ 1);
+    const uint64_t w = blk * WPB + wi;
+    const bool active = w < p.n_windows;
+    uint64_t begin = 0, end = 0;
+    if (active) window_bounds<P>(p, w, begin, end);
+    const WindowGeom<P> g(p.base, begin, end);
+    WinSrc src;
+    src.base = p.base;
+    src.a0 = s_range[s][0];
+    src.a1 = s_range[s][1];
+    src.stage_s = smem_u32(dsm) + s * stage_bytes;
+    const uint64_t vbyte = g.a0 * sizeof(Elem);  // byte offset of unit 1
+    src.vec_staged = vbyte >= src.a0 && vbyte + g.nv * 16 <= src.a1;
+    src.vec_s = src.stage_s + (uint32_t)(vbyte - src.a0);
+    src.vec_g = p.base + vbyte;
+    mbar_wait(&s_bar[s], (it >> 1) & 1);
+
+    // ---- value-only fold of this lane's share of the window
+    WinBest<Key> x;
+    x.clear();
+    for (uint32_t h = l; h < g.hc; h += L) {  // unit 0: unaligned head
+      Key k;
+      bool valid, is_nan;
+      P::classify(src.elem<Elem>(g.begin + h), k, valid, is_nan);
+      x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, 0);
+    }
+    if (src.vec_staged) {
+      staged_fold_vectors<P, L, true>(src, (uint32_t)g.nv, l, wi, x);
+    } else {
+      staged_fold_vectors<P, L, false>(src, (uint32_t)g.nv, l, wi, x);
+    }
+    for (uint32_t q = l; q < g.tc; q += L) {  // unit nv+1: sub-vector tail
+      Key k;
+      bool valid, is_nan;
+      P::classify(src.elem<Elem>(g.a0 + g.nv * WindowGeom<P>::VE + q), k, valid, is_nan);
+      x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, (uint32_t)g.nv + 1);
+    }
+    // ---- reduce inside the lane group (lexicographic on (key, unit))
+#pragma unroll
+    for (int m = L / 2; m >= 1; m >>= 1) {
+      const Key okmin = __shfl_xor_sync(0xFFFFFFFFu, x.kmin, m);
+      const Key okmax = __shfl_xor_sync(0xFFFFFFFFu, x.kmax, m);
+      const uint32_t oumin = __shfl_xor_sync(0xFFFFFFFFu, x.umin, m);
+      const uint32_t oumax = __shfl_xor_sync(0xFFFFFFFFu, x.umax, m);
+      if (okmin < x.kmin || (okmin == x.kmin && oumin < x.umin)) {
+        x.kmin = okmin;
+        x.umin = oumin;
+      }
+      if (okmax > x.kmax || (okmax == x.kmax && oumax < x.umax)) {
+        x.kmax = okmax;
+        x.umax = oumax;
+      }
+      if (P::TRACK_NAN) {
+        const uint32_t ounan = __shfl_xor_sync(0xFFFFFFFFu, x.unan, m);
+        x.unan = ounan < x.unan ? ounan : x.unan;
+      }
+    }
+    // ---- resolve the winning units: candidate c is handled by lane c % L of the group
+    uint64_t res[3] = {POS_NONE, POS_NONE, POS_NONE};
+    constexpr int NC = P::TRACK_NAN ? 3 : 2;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const uint32_t unit = c == 0 ? x.umin : (c == 1 ? x.umax : x.unan);
+      uint64_t r = POS_NONE;
+      if (active && unit != 0xFFFFFFFFu && l == (uint32_t)(c % L))
+        r = staged_locate<P>(src, g, unit, c, c == 0 ? x.kmin : x.kmax);
+      if (L > 1) r = __shfl_sync(0xFFFFFFFFu, r, (int)(lane - l) + (c % L));
+      res[c] = r;
+    }
+    if (active && l == 0) {
+      uint64_t imin, imax;
+      if (g.begin == g.end) {
+        imin = imax = AMM_NO_INDEX;
+      } else if (p.mode == MODE_RETURN && res[2] != POS_NONE) {
+        imin = imax = res[2];
+      } else if (res[0] == POS_NONE) {
+        imin = imax = g.begin;
+      } else {
+        imin = res[0];
+        imax = res[1];
+      }
+      if (out16) {  // 16-byte store, coalesced over the windows of the block
+        reinterpret_cast<ulonglong2*>(p.out)[w] = make_ulonglong2(imin, imax);
+      } else {
+        p.out[2 * w] = imin;
+        p.out[2 * w + 1] = imax;
+      }
+    }
+    __syncthreads();  // everyone is done with stage s: it may be refilled
+  }
+}
+
 // one CTA per window (large windows)
 template <class P, int THREADS, int UN>
 __global__ void __launch_bounds__(THREADS) argminmax_windows_cta_kernel(const WindowParams p) {

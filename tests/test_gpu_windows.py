@@ -84,3 +84,76 @@ def test_huge_windows_take_the_streaming_path():
     w8 = 50_000_000
     got = [tuple(r) for r in db.argminmax_windows(w8, 0).cpu().tolist()]
     assert got == _expected(b, [(0, w8), (w8, 2 * w8), (2 * w8, 3 * w8)], 0)
+
+
+@pytest.mark.parametrize("dt", G.ALL_DTYPES)
+def test_short_windows_every_lane_group(dt):
+    """Windows of 16 B ... 1 KiB take the TMA-staged kernel with 1, 2, 4 or 8 lanes per window
+    (windows_kernel.cuh): every lane-group size, aligned and unaligned bases, window sizes that
+    are / are not multiples of 16 bytes, NaN runs that cover whole windows, many ties."""
+    es = np.dtype(G.NP[dt]).itemsize
+    rng = np.random.default_rng(900 + G.ALL_DTYPES.index(dt))
+    n = 200_003
+    a = random_array(dt, n, rng)
+    ties = rng.integers(0, 3, n).astype(G.NP[dt])     # first occurrence inside short windows
+    if dt in G.FLOAT_DTYPES:
+        a[rng.integers(0, n, 3000)] = np.nan
+        a[70_000:70_900] = np.nan
+        ties[rng.integers(0, n, 3000)] = np.nan
+    for arr in (a, ties):
+        for off in (0, es, 16 - es if es < 16 else 0):
+            ds, _keep = to_device(arr, byte_offset=off)
+            for wbytes in (16, 48, 100, 128, 136, 256, 264, 512, 520, 1000, 1024):
+                window = max(2, wbytes // es)
+                nwin = -(-n // window)
+                bounds = [(w * window, min(n, (w + 1) * window)) for w in range(nwin)]
+                for mode in modes_for(dt):
+                    got = [tuple(r) for r in ds.argminmax_windows(window, mode).cpu().tolist()]
+                    assert got == _expected(arr, bounds, mode), (dt, off, window, mode)
+
+
+@pytest.mark.parametrize("dt", ["f32", "u8", "f64", "i16"])
+def test_short_ragged_windows_outliers_and_unordered_offsets(dt):
+    """Ragged short windows: (i) a few windows far larger than the staging buffer among many
+    tiny ones, (ii) offsets that are NOT ascending (reversed pairs give empty windows, windows may
+    overlap), (iii) an output buffer that is only 8-byte aligned.  The staged kernel must fall
+    back to global loads for whatever its stage does not hold."""
+    import torch
+    rng = np.random.default_rng(31)
+    n = 400_000
+    a = random_array(dt, n, rng)
+    ds, _keep = to_device(a, byte_offset=np.dtype(G.NP[dt]).itemsize)
+    # (i) mean window ~ 40 elements, three outliers of 30k elements
+    small = rng.integers(1, 80, 7000)
+    sizes = np.concatenate([small[:2000], [30_000], small[2000:4000], [30_000, 0, 0, 30_000], small[4000:]])
+    cuts = np.concatenate([[0], np.cumsum(sizes)])
+    cuts = cuts[cuts <= n]
+    cuts = np.concatenate([cuts, [n]])
+    offs = torch.from_numpy(cuts.astype(np.int64)).cuda()
+    bounds = list(zip(cuts[:-1].tolist(), cuts[1:].tolist()))
+    got = [tuple(r) for r in ds.argminmax_windows(offs, 0).cpu().tolist()]
+    assert got == _expected(a, bounds, 0)
+    # (ii) unordered offsets
+    cuts = rng.integers(0, n + 1, 5001)
+    cuts[::7] = np.sort(cuts[::7])
+    offs = torch.from_numpy(cuts.astype(np.int64)).cuda()
+    near = np.sort(rng.integers(0, n - 300, 3000))          # short, mostly ascending, some reversed
+    cuts2 = np.stack([near, near + rng.integers(-50, 200, 3000)], axis=1).reshape(-1)
+    cuts2 = np.clip(cuts2, 0, n)
+    for c in (cuts, cuts2):
+        offs = torch.from_numpy(c.astype(np.int64)).cuda()
+        bounds = [(min(b, min(e, n)), min(e, n)) for b, e in zip(c[:-1].tolist(), c[1:].tolist())]
+        got = [tuple(r) for r in ds.argminmax_windows(offs, 0).cpu().tolist()]
+        assert got == _expected(a, bounds, 0)
+    # (iii) output pointer that is 8- but not 16-byte aligned
+    from argminmax_b200 import DTYPES, lib
+    window = 24
+    nwin = -(-n // window)
+    out = torch.full((2 * nwin + 1,), -7, dtype=torch.int64, device="cuda:0")
+    rc = lib().amm_argminmax_fixed_windows(DTYPES[dt], ds.data_ptr, ds.n, window, 0,
+                                           ds.workspace.handle, ds.stream, out[1:].data_ptr())
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = [tuple(r) for r in out[1:].view(-1, 2).cpu().tolist()]
+    assert got == _expected(a, [(w * window, min(n, (w + 1) * window)) for w in range(nwin)], 0)
+    assert int(out[0]) == -7
