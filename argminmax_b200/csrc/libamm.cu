@@ -315,6 +315,7 @@ static int workspace_init(amm_workspace* ws, int device) {
   ws->publish_fence = getenv("AMM_PUBLISH_FENCE") ? atoi(getenv("AMM_PUBLISH_FENCE")) : 0;
   ws->pdl = getenv("AMM_PDL") ? atoi(getenv("AMM_PDL")) : 1;
   ws->win_staged = getenv("AMM_WIN_STAGED") ? atoi(getenv("AMM_WIN_STAGED")) : 1;
+  ws->win_chunked = getenv("AMM_WIN_CHUNKED") ? atoi(getenv("AMM_WIN_CHUNKED")) : 1;
   ws->win_lane_bytes = getenv("AMM_WIN_LANE_BYTES") ? atoi(getenv("AMM_WIN_LANE_BYTES")) : 128;
   if (ws->win_lane_bytes < 16 || ws->win_lane_bytes > 1024) ws->win_lane_bytes = 128;
   ws->max_grid = ws->sm_count * 32;
@@ -636,6 +637,117 @@ static int windows_huge(int dtype, const void* dev_ptr, uint64_t n, const uint64
   return AMM_OK;
 }
 
+constexpr int kNotApplicable = -12345;  // internal: "this path cannot take the input"
+
+// Window bounds on the host: fixed windows are computed, ragged ones are read back from the
+// device (one small copy + stream sync; only taken for few, large windows).
+static int host_window_bounds(const uint64_t* dev_offsets, uint64_t n, uint64_t window,
+                              uint64_t n_windows, cudaStream_t stream,
+                              std::vector<uint64_t>& begins, std::vector<uint64_t>& ends) {
+  begins.resize((size_t)n_windows);
+  ends.resize((size_t)n_windows);
+  if (dev_offsets) {
+    std::vector<uint64_t> offs((size_t)n_windows + 1);
+    AMM_CUDA(cudaMemcpyAsync(offs.data(), dev_offsets, sizeof(uint64_t) * offs.size(),
+                             cudaMemcpyDeviceToHost, stream));
+    AMM_CUDA(cudaStreamSynchronize(stream));
+    for (uint64_t w = 0; w < n_windows; ++w) {
+      const uint64_t e = offs[w + 1] < n ? offs[w + 1] : n;
+      begins[w] = offs[w] < e ? offs[w] : e;
+      ends[w] = e;
+    }
+  } else {
+    for (uint64_t w = 0; w < n_windows; ++w) {
+      uint64_t b = w * window, e = b + window;
+      e = e < n ? e : n;
+      begins[w] = b < e ? b : e;
+      ends[w] = e;
+    }
+  }
+  return AMM_OK;
+}
+
+// Few LARGE windows (1 MiB ... 64 MiB each, fewer than 4 per SM): one CTA per window would
+// leave most of the GPU idle and one streaming scan per window pays ~6 us each.  Instead every
+// window is cut into chunks (>= 128 KiB, one per resident CTA), the chunks run through the
+// ordinary windowed kernels as if they were windows -- thousands of them, so the whole GPU
+// streams -- and a combine kernel folds each window's chunk answers (first occurrence: the
+// lowest chunk wins ties).  One extra launch, < 1 % extra traffic.
+static int windows_chunked(int dtype, int slot, const void* dev_ptr, uint64_t n,
+                           const uint64_t* dev_offsets, uint64_t window, uint64_t n_windows,
+                           int mode, amm_workspace* ws, cudaStream_t stream, uint64_t* dev_out) {
+  const size_t es = amm_dtype_size(dtype);
+  std::vector<uint64_t> begins, ends;
+  int rc = host_window_bounds(dev_offsets, n, window, n_windows, stream, begins, ends);
+  if (rc) return rc;
+  for (uint64_t w = 1; w < n_windows; ++w)
+    if (begins[w] != ends[w - 1]) return kNotApplicable;  // not adjacent: caller falls back
+  // The chunks run one per CTA (argminmax_windows_cta_kernel<256>, sm_count x 8 resident CTAs,
+  // its fastest regime: ~1 MiB windows, all resident at once).  Size them so that ALL chunks fit
+  // into one resident round -- a second, mostly empty round would double the kernel time.
+  const uint64_t slots = (uint64_t)ws->sm_count * 8;
+  const uint64_t span = ends[n_windows - 1] - begins[0];
+  uint64_t chunk = (span + (slots - n_windows) - 1) / (slots - n_windows);  // elements per chunk
+  const uint64_t min_chunk = ((uint64_t)128 << 10) / es;
+  if (chunk < min_chunk) chunk = min_chunk;
+  // chunk k = [cuts[k], cuts[k+1]); window w owns chunks [first[w], first[w+1]) -- windows are
+  // adjacent, so the last cut of one window is the first cut of the next
+  std::vector<uint64_t> cuts, first((size_t)n_windows + 1);
+  cuts.reserve((size_t)(span / chunk) + 2 * (size_t)n_windows + 2);
+  cuts.push_back(begins[0]);
+  for (uint64_t w = 0; w < n_windows; ++w) {
+    first[w] = cuts.size() - 1;
+    const uint64_t len = ends[w] - begins[w];
+    if (len == 0) continue;
+    // equal pieces (a short last piece would leave its CTA idle while the others finish);
+    // multiples of 256 elements keep the piece starts vector-aligned
+    const uint64_t pieces = (len + chunk - 1) / chunk;
+    const uint64_t piece = ((len + pieces - 1) / pieces + 255) / 256 * 256;
+    for (uint64_t b = begins[w] + piece; b < ends[w]; b += piece) cuts.push_back(b);
+    cuts.push_back(ends[w]);
+  }
+  first[n_windows] = cuts.size() - 1;
+  const uint64_t n_chunks = cuts.size() - 1;
+  if (n_chunks == 0) return AMM_ERR_ARG;
+  // scratch on the device: cuts | first | pairs
+  const size_t need = sizeof(uint64_t) * (cuts.size() + first.size() + 2 * (size_t)n_chunks);
+  if (ws->win_scratch_bytes < need) {
+    if (ws->win_scratch) AMM_CUDA(cudaFree(ws->win_scratch));
+    ws->win_scratch = nullptr;
+    ws->win_scratch_bytes = 0;
+    AMM_CUDA(cudaMalloc(&ws->win_scratch, need));
+    ws->win_scratch_bytes = need;
+  }
+  uint64_t* d_cuts = (uint64_t*)ws->win_scratch;
+  uint64_t* d_first = d_cuts + cuts.size();
+  uint64_t* d_pairs = d_first + first.size();
+  AMM_CUDA(cudaMemcpyAsync(d_cuts, cuts.data(), sizeof(uint64_t) * cuts.size(),
+                           cudaMemcpyHostToDevice, stream));
+  AMM_CUDA(cudaMemcpyAsync(d_first, first.data(), sizeof(uint64_t) * first.size(),
+                           cudaMemcpyHostToDevice, stream));
+  WindowParams pc;
+  pc.window = 0;
+  pc.base = (const uint8_t*)dev_ptr;
+  pc.n = n;
+  pc.offsets = d_cuts;
+  pc.n_windows = n_chunks;
+  pc.out = d_pairs;
+  pc.mode = mode;
+  rc = windows_slot(slot, ws, pc, n / n_chunks, stream);
+  if (rc) return rc;
+  WindowParams pw;
+  pw.base = (const uint8_t*)dev_ptr;
+  pw.n = n;
+  pw.offsets = dev_offsets;
+  pw.window = window;
+  pw.n_windows = n_windows;
+  pw.out = dev_out;
+  pw.mode = mode;
+  pw.chunk_first = d_first;
+  pw.chunk_pairs = d_pairs;
+  return windows_slot(slot, ws, pw, n / n_windows, stream);
+}
+
 static int windows_common(int dtype, const void* dev_ptr, uint64_t n, const uint64_t* dev_offsets,
                           uint64_t window, uint64_t n_windows, int mode, amm_workspace* ws,
                           void* stream, uint64_t* dev_out) {
@@ -667,6 +779,15 @@ static int windows_common(int dtype, const void* dev_ptr, uint64_t n, const uint
   const double t_cta_us = total_bytes / (busy_ctas * 40.0e3);
   const double per_scan_us = win_bytes / 7.0e6 > 6.0 ? win_bytes / 7.0e6 : 6.0;
   const double t_scan_us = (double)n_windows * per_scan_us;
+  // ... unless the windows are of middling size: then chunks of them fill the GPU in one launch
+  const double t_chunk_us = total_bytes / (amm_dtype_size(dtype) == 8 ? 4.9e6 : 5.8e6) + 8.0;
+  const double t_huge_us = (double)n_windows * (win_bytes / 6.9e6 + 0.9 > 6.5 ? win_bytes / 6.9e6 + 0.9 : 6.5);
+  if (ws->win_chunked && n_windows < (uint64_t)ws->sm_count * 4 && win_bytes >= (double)(1 << 20) &&
+      t_chunk_us < t_huge_us) {
+    rc = windows_chunked(dtype, slot, dev_ptr, n, dev_offsets, window, n_windows, mode, ws,
+                         (cudaStream_t)stream, dev_out);
+    if (rc != kNotApplicable) return rc;  // windows not adjacent (unordered offsets): paths below
+  }
   if (n_windows <= 65536 && win_bytes >= (double)(1 << 20) && t_scan_us < t_cta_us)
     return windows_huge(dtype, dev_ptr, n, dev_offsets, window, n_windows, mode, ws,
                         (cudaStream_t)stream, dev_out);

@@ -175,6 +175,14 @@ static int launch_windows(amm_workspace* ws, const WindowParams& p, uint64_t mea
                           cudaStream_t stream) {
   const uint64_t cap = (uint64_t)ws->sm_count * 8;
   uint64_t grid;
+  if (p.chunk_first != nullptr) {  // combine step of the chunked form
+    grid = (p.n_windows + 7) / 8;
+    grid = grid > cap ? cap : (grid < 1 ? 1 : grid);
+    argminmax_windows_combine_kernel<P><<<(unsigned)grid, 256, 0, stream>>>(p);
+    AMM_CUDA(cudaGetLastError());
+    ws->launches += 1;
+    return AMM_OK;
+  }
   const uint64_t mean_bytes = mean_window * sizeof(typename P::Elem);
   const uint64_t lane_bytes = (uint64_t)ws->win_lane_bytes;  // target bytes per lane
   if (mean_bytes <= 8 * lane_bytes && mean_bytes <= 1024 && ws->win_staged) {

@@ -21,6 +21,11 @@ struct WindowParams {
   uint64_t n_windows;
   uint64_t* out;            // 2 * n_windows: (argmin, argmax) per window, absolute indices
   int mode;
+  // chunked form (few large windows, see windows_chunked in libamm.cu): when chunk_first is set
+  // the launch is the COMBINE step -- window w owns chunks [chunk_first[w], chunk_first[w+1]),
+  // whose (argmin, argmax) pairs are in chunk_pairs
+  const uint64_t* chunk_first = nullptr;
+  const uint64_t* chunk_pairs = nullptr;
 };
 
 template <class P>
@@ -591,6 +596,56 @@ __global__ void __launch_bounds__(THREADS)
       }
     }
     __syncthreads();  // everyone is done with stage s: it may be refilled
+  }
+}
+
+// Combine step of the chunked form: one warp per window folds the per-chunk answers.  Only
+// indices were kept per chunk; the candidates' values are re-read (two elements per chunk).
+// Chunks are visited in ascending order and merged lexicographically on (key, index), i.e. the
+// lowest chunk wins ties = first occurrence in the window (src/simd/generic.rs:513-520 merges
+// its chunks the same way).
+template <class P>
+__global__ void __launch_bounds__(256) argminmax_windows_combine_kernel(const WindowParams p) {
+  using Elem = typename P::Elem;
+  using Key = typename P::Key;
+  const Elem* e = reinterpret_cast<const Elem*>(p.base);
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+  for (uint64_t w = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < p.n_windows;
+       w += warps) {
+    uint64_t begin, end;
+    window_bounds<P>(p, w, begin, end);
+    Best<Key> x;
+    x.clear();
+    for (uint64_t k = p.chunk_first[w] + lane; k < p.chunk_first[w + 1]; k += 32) {
+      const uint64_t i0 = p.chunk_pairs[2 * k], i1 = p.chunk_pairs[2 * k + 1];
+      if (i0 == AMM_NO_INDEX) continue;  // empty chunk
+      Key k0, k1;
+      bool v0, v1, n0, n1;
+      P::classify(e[i0], k0, v0, n0);
+      P::classify(e[i1], k1, v1, n1);
+      if (v0) x.merge_min(k0, i0);
+      if (v1) x.merge_max(k1, i1);
+      // return-NaN: a chunk that holds a NaN answers (first NaN, first NaN)
+      if (P::TRACK_NAN && n0 && i0 < x.pnan) x.pnan = i0;
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) x.merge(shfl_xor(x, m));
+    if (lane == 0) {
+      uint64_t imin, imax;
+      if (begin == end) {
+        imin = imax = AMM_NO_INDEX;
+      } else if (p.mode == MODE_RETURN && x.pnan != POS_NONE) {
+        imin = imax = x.pnan;
+      } else if (x.pmin == POS_NONE) {
+        imin = imax = begin;  // all NaN, ignore mode
+      } else {
+        imin = x.pmin;
+        imax = x.pmax;
+      }
+      p.out[2 * w] = imin;
+      p.out[2 * w + 1] = imax;
+    }
   }
 }
 

@@ -118,6 +118,37 @@ class ClockSampler(threading.Thread):
                 "power_w_max": round(max(watts), 1) if watts else None}
 
 
+# ------------------------------------------------------------------------ NUMA
+def bind_to_gpu_numa_node(torch, index: int) -> dict:
+    """Run this rank (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA
+    node its GPU hangs off -- what `numactl --cpunodebind` does for one-rank-per-GPU jobs.  With 8
+    ranks streaming host memory to 8 GPUs at once, buffers that all sit on one socket make the
+    other socket's GPUs pull their input across the inter-socket link.  No-op when sysfs has no
+    NUMA information (single-node VMs report -1)."""
+    info = {"node": None, "cpus": None}
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        sys_id = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{sys_id}/numa_node") as f:
+            node = int(f.read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+    except Exception as e:  # noqa: BLE001 - placement is an optimisation, never a failure
+        info["error"] = type(e).__name__
+    return info
+
+
 # ------------------------------------------------------------------------ data
 def make_device_data(torch, device, n: int, seed: int):
     """Uniform random bit patterns viewed as f32, NaN -> 0.0 (dev_utils/src/utils.rs:55-77)."""
@@ -249,6 +280,7 @@ def main() -> int:
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=device)
     amm.lib()  # fail loudly if the extension is missing
+    numa = bind_to_gpu_numa_node(torch, local_rank)
 
     n = args.elems
     nbytes = n * 4
@@ -426,6 +458,7 @@ def main() -> int:
                                if sharded.exchange == "peer" else
                                "nccl all_gather of 64-byte records + combine kernel"),
                 "tuning": tuning, "grid": ll["grid"], "block": ll["threads"],
+                "host_numa_binding": numa,
             },
             "elements_per_s": round(world * n / (ms_per_step / 1e3), 1),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

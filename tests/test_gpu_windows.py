@@ -157,3 +157,58 @@ def test_short_ragged_windows_outliers_and_unordered_offsets(dt):
     got = [tuple(r) for r in out[1:].view(-1, 2).cpu().tolist()]
     assert got == _expected(a, [(w * window, min(n, (w + 1) * window)) for w in range(nwin)], 0)
     assert int(out[0]) == -7
+
+
+@pytest.mark.parametrize("dt", ["f32", "u8", "f64", "f16"])
+def test_few_large_windows_are_chunked(dt):
+    """Fewer than 4 windows per SM of 1-64 MiB each are cut into chunks that run through the
+    ordinary window kernels, plus a combine kernel (windows_chunked in libamm.cu): duplicate
+    extremes in different chunks of one window (first must win), NaNs, an all-NaN chunk, ragged
+    windows with empty ones in between; chunked == not chunked == oracle."""
+    import torch
+
+    from argminmax_b200 import Workspace
+    es = np.dtype(G.NP[dt]).itemsize
+    rng = np.random.default_rng(1200 + es)
+    n = (48 << 20) // es + 12_345
+    a = random_array(dt, n, rng)
+    T = G.NP[dt]
+    if dt in G.FLOAT_DTYPES:
+        a[~np.isfinite(a)] = 0
+        big = T(6.0e4)
+        a[np.abs(a) >= big] = 0
+        lo, hi = -big, big
+    else:
+        info = np.iinfo(T)
+        lo, hi = T(info.min), T(info.max)
+        mid = T(info.min // 2 + info.max // 2 + 1)
+        a[a == lo] = mid
+        a[a == hi] = mid
+    window = (5 << 20) // es + 77          # ~5 MiB windows, unaligned length
+    nwin = -(-n // window)
+    for w in range(nwin):                   # duplicate extremes far apart inside every window
+        b, e = w * window, min(n, (w + 1) * window)
+        p = np.sort(rng.choice(np.arange(b, e), 6, replace=False))
+        a[p[[1, 3, 5]]] = lo
+        a[p[[0, 2, 4]]] = hi
+    if dt in G.FLOAT_DTYPES:
+        a[window + 100_000: window + 100_000 + (200 << 10) // es] = np.nan   # a whole chunk of NaN
+        a[3 * window + 5] = np.nan
+    ds, _keep = to_device(a, byte_offset=es)
+    fixed = [(w * window, min(n, (w + 1) * window)) for w in range(nwin)]
+    cuts = np.array([0, 0, 2_000_000 // es * 4, 2_000_000 // es * 4, n // 2, n - 3, n, n], dtype=np.int64)
+    ragged = list(zip(cuts[:-1].tolist(), cuts[1:].tolist()))
+    offs = torch.from_numpy(cuts).cuda()
+    import os
+    os.environ["AMM_WIN_CHUNKED"] = "0"     # read when a workspace is created
+    try:
+        plain = Workspace(0)                # the same windows through the un-chunked paths
+    finally:
+        del os.environ["AMM_WIN_CHUNKED"]
+    for mode in modes_for(dt):
+        exp_fixed, exp_ragged = _expected(a, fixed, mode), _expected(a, ragged, mode)
+        for ws in (ds.workspace, plain):
+            ds._ws = ws
+            assert [tuple(r) for r in ds.argminmax_windows(window, mode).cpu().tolist()] == exp_fixed
+            assert [tuple(r) for r in ds.argminmax_windows(offs, mode).cpu().tolist()] == exp_ragged
+    plain.close()
