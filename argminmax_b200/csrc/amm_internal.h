@@ -34,8 +34,11 @@ struct amm_workspace {
   int variant;      // load shape, see kVariants in scan_launch.cuh
   int eff_threads, eff_ctas_per_sm, eff_variant;  // what the last streaming launch used
   int max_grid;
-  uint64_t direct_bytes;  // inputs up to this size take the one-pass latency kernel
+  uint64_t direct_bytes;  // inputs up to this size take the one-pass latency kernel ...
+  int direct_auto;        // ... unless 1: size rule per key width (see launch_variant)
   int direct_threads, direct_ctas_per_sm;
+  int direct_vecs_per_thread;  // target vectors per thread when sizing the latency kernel's grid
+  int direct_packed;      // 32-bit keys: packed-word atomics instead of partials (AMM_DIRECT_PACKED=0: off)
   int occupancy[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];      // cached CTAs/SM ...
   int occupancy_threads[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // ... for this CTA size
   void* partials;            // max_grid x 64 B

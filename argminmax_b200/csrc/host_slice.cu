@@ -83,6 +83,9 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
   for (int i = 0; i < 2; ++i) {
     amm_workspace_set_tuning(p->child[i], ws->threads, ws->ctas_per_sm, ws->variant);
     p->child[i]->direct_bytes = ws->direct_bytes;
+    p->child[i]->direct_auto = ws->direct_auto;
+    p->child[i]->direct_packed = ws->direct_packed;
+    p->child[i]->direct_vecs_per_thread = ws->direct_vecs_per_thread;
     p->child[i]->pdl = ws->pdl;
     p->child[i]->direct_threads = ws->direct_threads;
     p->child[i]->direct_ctas_per_sm = ws->direct_ctas_per_sm;

@@ -306,9 +306,16 @@ static int workspace_init(amm_workspace* ws, int device) {
   ws->direct_threads = 256;
   ws->direct_ctas_per_sm = 2;
   // experiment knobs (tools/, profiling); the defaults are the tuned values
-  if (getenv("AMM_DIRECT_BYTES")) ws->direct_bytes = strtoull(getenv("AMM_DIRECT_BYTES"), nullptr, 10);
+  ws->direct_auto = 1;
+  if (getenv("AMM_DIRECT_BYTES")) {
+    ws->direct_bytes = strtoull(getenv("AMM_DIRECT_BYTES"), nullptr, 10);
+    ws->direct_auto = 0;
+  }
   if (getenv("AMM_DIRECT_THREADS")) ws->direct_threads = atoi(getenv("AMM_DIRECT_THREADS"));
   if (getenv("AMM_DIRECT_CTAS")) ws->direct_ctas_per_sm = atoi(getenv("AMM_DIRECT_CTAS"));
+  ws->direct_packed = getenv("AMM_DIRECT_PACKED") ? atoi(getenv("AMM_DIRECT_PACKED")) : 1;
+  ws->direct_vecs_per_thread = getenv("AMM_DIRECT_VPT") ? atoi(getenv("AMM_DIRECT_VPT")) : 1;
+  if (ws->direct_vecs_per_thread < 1 || ws->direct_vecs_per_thread > 16) ws->direct_vecs_per_thread = 1;
   if (ws->direct_threads < 64 || ws->direct_threads > MAX_THREADS || ws->direct_threads % 32)
     ws->direct_threads = 256;
   if (ws->direct_ctas_per_sm < 1 || ws->direct_ctas_per_sm > 32) ws->direct_ctas_per_sm = 2;
@@ -323,6 +330,10 @@ static int workspace_init(amm_workspace* ws, int device) {
   AMM_CUDA(cudaMalloc(&ws->partials, (size_t)ws->max_grid * 64));
   AMM_CUDA(cudaMalloc((void**)&ws->ticket, 256));
   AMM_CUDA(cudaMemset(ws->ticket, 0, 256));
+  {  // packed candidate words of the latency kernel start at their identities (packed_finish)
+    const unsigned long long ident[3] = {PACK_MIN_NONE, PACK_MAX_NONE, POS_NONE};
+    AMM_CUDA(cudaMemcpy(ws->ticket + 16, ident, sizeof(ident), cudaMemcpyHostToDevice));
+  }
   AMM_CUDA(cudaMalloc((void**)&ws->rec_dev, sizeof(amm_record)));
   AMM_CUDA(cudaMemset(ws->rec_dev, 0, sizeof(amm_record)));
   AMM_CUDA(cudaHostAlloc((void**)&ws->rec_host, 128, cudaHostAllocMapped));
@@ -926,6 +937,7 @@ int amm_workspace_set_pipelined(amm_workspace* ws, int on) {
 int amm_workspace_set_direct_threshold(amm_workspace* ws, uint64_t bytes) {
   if (!ws) return AMM_ERR_ARG;
   ws->direct_bytes = bytes;
+  ws->direct_auto = 0;
   return AMM_OK;
 }
 

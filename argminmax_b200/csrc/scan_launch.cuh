@@ -95,17 +95,29 @@ static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) 
   p.n_vec = (p.n - head) / vec_elems;
   p.tail_start = head + p.n_vec * vec_elems;
   const int threads = ws->direct_threads;
-  const uint64_t per_cta = (uint64_t)threads * 4;  // vectors per CTA per trip
+  // Latency, not throughput: as long as CTAs are available give every thread ONE vector (its
+  // exact per-element tracking is a serial chain of ~25 instructions per element); only
+  // beyond sm_count x direct_ctas_per_sm CTAs do threads loop (4 vectors in flight per trip).
+  const uint64_t per_cta = (uint64_t)threads * (uint64_t)ws->direct_vecs_per_thread;
   uint64_t grid = (p.n_vec + per_cta - 1) / per_cta;
+  // up to 16 elements per thread ONE CTA is quicker than several: a second CTA brings in the
+  // cross-CTA round trip (~1.3 us)
+  if (p.n <= (uint64_t)threads * 16) grid = 1;
   const uint64_t cap = (uint64_t)ws->sm_count * (uint64_t)ws->direct_ctas_per_sm;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  if (p.world > 1)
+  if (p.world > 1) {
     AMM_CUDA(launch_scan(argminmax_direct_kernel<P, true>, (unsigned)grid, (unsigned)threads, stream,
                          p, ws->pdl != 0));
-  else
+  } else if (sizeof(typename P::Key) == 4 && p.n < 0xFFFFFFFEull && ws->direct_packed) {
+    // 32-bit keys: candidates travel as one packed 64-bit word (see packed_finish)
+    if constexpr (sizeof(typename P::Key) == 4)
+      AMM_CUDA(launch_scan(argminmax_direct_kernel<P, false, true>, (unsigned)grid,
+                           (unsigned)threads, stream, p, ws->pdl != 0));
+  } else {
     AMM_CUDA(launch_scan(argminmax_direct_kernel<P, false>, (unsigned)grid, (unsigned)threads,
                          stream, p, ws->pdl != 0));
+  }
   ws->last_grid = (int)grid;
   ws->last_threads = threads;
   ws->launches += 1;
@@ -115,7 +127,13 @@ static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) 
 template <class P>
 static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStream_t stream) {
   const uint64_t bytes = p.n * sizeof(typename P::Elem);
-  if (bytes <= ws->direct_bytes) return launch_direct<P>(ws, p, stream);
+  // Latency kernel below the measured crossover with the streaming kernel (tools/latency_c.py):
+  // 2^20 elements for 32-bit keys (packed-word finish), 2^16 for 64-bit keys; an explicit
+  // threshold (amm_workspace_set_direct_threshold / AMM_DIRECT_BYTES) replaces the rule.
+  const bool direct = ws->direct_auto
+                          ? p.n <= (sizeof(typename P::Key) == 4 ? (1ull << 20) : (1ull << 16))
+                          : bytes <= ws->direct_bytes;
+  if (direct) return launch_direct<P>(ws, p, stream);
   // Automatic geometry (B200 sweeps, profiles/r01_sweeps.md): 256-bit loads and a deep grid
   // win on HBM-sized inputs; below ~0.5 GiB the fixed tail matters more and 128-bit loads
   // with 2 CTAs/SM finish sooner.

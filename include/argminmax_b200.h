@@ -275,8 +275,10 @@ int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, in
    NOT produced by the kernel enqueued immediately before it on the same stream (memcpys and
    earlier kernels are fine).  Off by default; results and their order are unchanged. */
 int amm_workspace_set_pipelined(amm_workspace* ws, int on);
-/* Inputs of at most `bytes` take the one-pass latency kernel (exact per-element tracking, no
-   second phase) instead of the streaming kernel; 0 disables it. */
+/* Small inputs take the one-pass latency kernel (exact per-element tracking, no second phase)
+   instead of the streaming kernel: by default up to 2^20 elements for 1/2/4-byte dtypes and
+   2^16 for 8-byte dtypes (the measured crossovers).  This call replaces that rule by "inputs of
+   at most `bytes`"; 0 disables the latency kernel. */
 int amm_workspace_set_direct_threshold(amm_workspace* ws, uint64_t bytes);
 int amm_workspace_get_tuning(const amm_workspace* ws, int* threads, int* ctas_per_sm, int* variant,
                              int* sm_count);
