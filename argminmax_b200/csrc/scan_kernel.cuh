@@ -303,16 +303,18 @@ __device__ __forceinline__ uint64_t record_checksum(const amm_record& r) {
 __device__ __forceinline__ void publish_record(const ScanParams& p, const amm_record& r) {
   *p.rec_dev = r;
   if (p.rec_host != nullptr) {
-    volatile uint64_t* h = reinterpret_cast<volatile uint64_t*>(p.rec_host);
-    h[0] = (uint64_t)r.min_key;
-    h[1] = r.min_idx;
-    h[2] = (uint64_t)r.max_key;
-    h[3] = r.max_idx;
-    h[4] = r.nan_idx;
-    h[5] = r.flags;
-    h[6] = r.n;
-    h[7] = r.seq;
-    h[8] = record_checksum(r);
+    // 16-byte stores: every store to mapped host memory is its own PCIe write, and the host
+    // needs the LAST one to have landed (4 x 16 B + 8 B instead of 9 x 8 B: -0.25 us per call,
+    // tools/exp/latency_floor.cu cases G/H)
+    uint64_t* h = reinterpret_cast<uint64_t*>(p.rec_host);
+    const uint64_t w[8] = {(uint64_t)r.min_key, r.min_idx, (uint64_t)r.max_key, r.max_idx,
+                           r.nan_idx,           r.flags,   r.n,                 r.seq};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(h + 2 * i), "l"(w[2 * i]),
+                   "l"(w[2 * i + 1])
+                   : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(h + 8), "l"(record_checksum(r)) : "memory");
     if (p.publish_fence) __threadfence_system();
   }
 }

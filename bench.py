@@ -375,6 +375,11 @@ def main() -> int:
                         "consecutive steps pipelined (PDL), which hides each kernel's fold/publish tail",
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)}
 
+    # the clock sampler belongs to the timed regions above; its NVML polling thread would
+    # contend with the launch path of the latency probe below
+    sampler.stop_flag = True
+    sampler.join(timeout=2.0)
+
     # ---- small-n latency: us per call at 1M elements, synchronous C-ABI call timed inside the
     #      library (amm_measure_call_latency: host wall clock, no Python in the loop)
     import ctypes
