@@ -170,19 +170,41 @@ static int launch_windows_staged(amm_workspace* ws, const WindowParams& p, uint6
                                  cudaStream_t stream) {
   constexpr int THREADS = 128;
   constexpr uint64_t WPB = THREADS / L;
+  constexpr uint64_t ES = sizeof(typename P::Elem);
+  auto grid_for = [&](uint64_t n_windows) {
+    const uint64_t n_blocks = (n_windows + WPB - 1) / WPB;
+    uint64_t grid = (uint64_t)ws->sm_count * 6;
+    grid = n_blocks < grid ? n_blocks : grid;
+    return (unsigned)(grid < 1 ? 1 : grid);
+  };
+  WindowParams rest = p;  // what the general kernel still has to do
+  // Fixed windows of a multiple of 16 bytes on a 16-byte aligned array: all FULL windows take
+  // the geometry-free instantiation; a last, shorter window (if any) goes to the general one.
+  if (p.offsets == nullptr && p.w_first == 0 && (p.window * ES) % 16 == 0 &&
+      ((uintptr_t)p.base % 16) == 0 && ws->win_fast) {
+    const uint64_t n_full = p.n / p.window;
+    if (n_full > 0) {
+      WindowParams pf = p;
+      pf.n_windows = n_full;
+      const uint64_t stage = WPB * p.window * ES;  // <= 128 x 128 B = 16 KiB by the dispatch rule
+      argminmax_windows_staged_kernel<P, L, THREADS, true>
+          <<<grid_for(n_full), THREADS, (size_t)(2 * stage), stream>>>(pf, (uint32_t)stage);
+      AMM_CUDA(cudaGetLastError());
+      ws->launches += 1;
+    }
+    if (n_full >= p.n_windows) return AMM_OK;
+    rest.w_first = n_full;
+    rest.n_windows = p.n_windows - n_full;
+  }
   // stage = the bytes of one block of windows (+ alignment slack); ragged windows get 2x the
   // mean (what does not fit is read from global memory by the kernel)
-  const uint64_t fixed_bytes = (p.window < p.n ? p.window : p.n) * sizeof(typename P::Elem);
+  const uint64_t fixed_bytes = (p.window < p.n ? p.window : p.n) * ES;
   uint64_t stage = (p.offsets ? 2 * mean_bytes : fixed_bytes) * WPB + 64;
   stage = (stage + 127) / 128 * 128;
   if (stage < 1024) stage = 1024;
   if (stage > 20480) stage = 20480;  // 2 stages + static smem stay below the 48 KB default limit
-  const uint64_t n_blocks = (p.n_windows + WPB - 1) / WPB;
-  uint64_t grid = (uint64_t)ws->sm_count * 6;
-  grid = n_blocks < grid ? n_blocks : grid;
-  grid = grid < 1 ? 1 : grid;
   argminmax_windows_staged_kernel<P, L, THREADS>
-      <<<(unsigned)grid, THREADS, (size_t)(2 * stage), stream>>>(p, (uint32_t)stage);
+      <<<grid_for(rest.n_windows), THREADS, (size_t)(2 * stage), stream>>>(rest, (uint32_t)stage);
   AMM_CUDA(cudaGetLastError());
   ws->launches += 1;
   return AMM_OK;

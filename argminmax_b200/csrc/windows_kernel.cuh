@@ -26,6 +26,9 @@ struct WindowParams {
   // whose (argmin, argmax) pairs are in chunk_pairs
   const uint64_t* chunk_first = nullptr;
   const uint64_t* chunk_pairs = nullptr;
+  // fixed windows only: id of the first window this launch handles (a launch may cover a
+  // sub-range [w_first, w_first + n_windows) of the windows of the array)
+  uint64_t w_first = 0;
 };
 
 template <class P>
@@ -35,7 +38,7 @@ __device__ __forceinline__ void window_bounds(const WindowParams& p, uint64_t w,
     b = p.offsets[w];
     e = p.offsets[w + 1];
   } else {
-    b = w * p.window;
+    b = (p.w_first + w) * p.window;
     e = b + p.window;
   }
   e = e < p.n ? e : p.n;
@@ -59,6 +62,9 @@ struct WindowGeom {
   uint64_t a0;          // first element of unit 1 (16-byte aligned address)
   uint32_t hc, tc;      // head / tail element counts (< VE)
   uint64_t nv;          // aligned vectors
+  // a window that is exactly `vecs` aligned 16-byte vectors: no head, no tail
+  __device__ __forceinline__ WindowGeom(uint64_t b, uint32_t vecs)
+      : begin(b), end(b + (uint64_t)vecs * VE), a0(b), hc(0), tc(0), nv(vecs) {}
   __device__ __forceinline__ WindowGeom(const uint8_t* base, uint64_t b, uint64_t e)
       : begin(b), end(e) {
     const uint64_t addr = (uint64_t)(uintptr_t)base + b * sizeof(typename P::Elem);
@@ -187,8 +193,8 @@ __device__ __forceinline__ void window_locate_store(const WindowParams& p, uint6
       imin = res[0];
       imax = res[1];
     }
-    p.out[2 * w] = imin;
-    p.out[2 * w + 1] = imax;
+    p.out[2 * (p.w_first + w)] = imin;
+    p.out[2 * (p.w_first + w) + 1] = imax;
   }
 }
 
@@ -417,7 +423,7 @@ __device__ __forceinline__ void staged_fold_vectors(const WinSrc& src, uint32_t 
 
 // first element of unit `u` of window `g` that matches candidate `c` (0: key == kmin, 1: key ==
 // kmax, 2: NaN), or POS_NONE.  One thread, in registers for the 16-byte units.
-template <class P>
+template <class P, bool FAST>
 __device__ __forceinline__ uint64_t staged_locate(const WinSrc& src, const WindowGeom<P>& g,
                                                   uint32_t unit, int c, typename P::Key want) {
   using Elem = typename P::Elem;
@@ -431,8 +437,15 @@ __device__ __forceinline__ uint64_t staged_locate(const WinSrc& src, const Windo
   };
   uint64_t first;
   uint32_t count;
-  g.unit_range(unit, first, count);
   int found = -1;
+  if (FAST) {  // every unit is a staged vector
+    uint32_t w[4];
+    src.vec<true>(unit - 1, w);
+#pragma unroll
+    for (int e = VE - 1; e >= 0; --e) found = is_hit(vec_elem<P, 4>(w, e)) ? e : found;
+    return found < 0 ? POS_NONE : g.begin + (uint64_t)(unit - 1) * VE + (uint64_t)found;
+  }
+  g.unit_range(unit, first, count);
   if (unit >= 1 && unit <= g.nv) {
     uint32_t w[4];
     if (src.vec_staged) {
@@ -448,7 +461,10 @@ __device__ __forceinline__ uint64_t staged_locate(const WinSrc& src, const Windo
   return found < 0 ? POS_NONE : first + (uint64_t)found;
 }
 
-template <class P, int L, int THREADS>
+// FAST: fixed windows whose size is a multiple of 16 bytes on a 16-byte aligned array, full
+// windows only -- every window is exactly p.window / VE staged vectors, so all the per-window
+// geometry (head / tail, staged-range tests, clamps) disappears.
+template <class P, int L, int THREADS, bool FAST = false>
 __global__ void __launch_bounds__(THREADS)
     argminmax_windows_staged_kernel(const WindowParams p, const uint32_t stage_bytes) {
   using Elem = typename P::Elem;
@@ -463,7 +479,17 @@ __global__ void __launch_bounds__(THREADS)
   const bool out16 = (((uint64_t)(uintptr_t)p.out) & 15) == 0;
 
   // thread 0: staged byte range of block `blk`, published in s_range[s], and the copy itself
+  const uint32_t wvec = FAST ? (uint32_t)(p.window / WindowGeom<P>::VE) : 0;  // vectors per window
   auto issue = [&](uint64_t blk, uint32_t s) {
+    if (FAST) {
+      const uint64_t wb = blk * WPB;
+      const uint64_t cnt = wb + WPB < p.n_windows ? WPB : p.n_windows - wb;
+      const uint32_t bytes = (uint32_t)(cnt * wvec * 16);
+      mbar_arrive_expect_tx(&s_bar[s], bytes);
+      tma_bulk_g2s(dsm + (size_t)s * stage_bytes,
+                   p.base + ((p.w_first + wb) * p.window) * sizeof(Elem), bytes, &s_bar[s]);
+      return;
+    }
     const uint64_t abase = (uint64_t)(uintptr_t)p.base;
     const uint64_t n_bytes = p.n * sizeof(Elem);
     // 16-byte aligned interior of the array, as byte offsets relative to base
@@ -510,39 +536,54 @@ __global__ void __launch_bounds__(THREADS)
     if (tid == 0 && blk + gridDim.x < n_blocks) issue(blk + gridDim.x, s ^ 1);
     const uint64_t w = blk * WPB + wi;
     const bool active = w < p.n_windows;
-    uint64_t begin = 0, end = 0;
-    if (active) window_bounds<P>(p, w, begin, end);
-    const WindowGeom<P> g(p.base, begin, end);
     WinSrc src;
     src.base = p.base;
-    src.a0 = s_range[s][0];
-    src.a1 = s_range[s][1];
     src.stage_s = smem_u32(dsm) + s * stage_bytes;
-    const uint64_t vbyte = g.a0 * sizeof(Elem);  // byte offset of unit 1
-    src.vec_staged = vbyte >= src.a0 && vbyte + g.nv * 16 <= src.a1;
-    src.vec_s = src.stage_s + (uint32_t)(vbyte - src.a0);
-    src.vec_g = p.base + vbyte;
+    const WindowGeom<P> g = [&]() {
+      if constexpr (FAST) {
+        src.a0 = src.a1 = 0;
+        src.vec_staged = true;
+        src.vec_s = src.stage_s + wi * wvec * 16u;
+        src.vec_g = nullptr;
+        return WindowGeom<P>((p.w_first + w) * p.window, active ? wvec : 0u);
+      } else {
+        uint64_t begin = 0, end = 0;
+        if (active) window_bounds<P>(p, w, begin, end);
+        const WindowGeom<P> gg(p.base, begin, end);
+        src.a0 = s_range[s][0];
+        src.a1 = s_range[s][1];
+        const uint64_t vbyte = gg.a0 * sizeof(Elem);  // byte offset of unit 1
+        src.vec_staged = vbyte >= src.a0 && vbyte + gg.nv * 16 <= src.a1;
+        src.vec_s = src.stage_s + (uint32_t)(vbyte - src.a0);
+        src.vec_g = p.base + vbyte;
+        return gg;
+      }
+    }();
     mbar_wait(&s_bar[s], (it >> 1) & 1);
 
     // ---- value-only fold of this lane's share of the window
     WinBest<Key> x;
     x.clear();
-    for (uint32_t h = l; h < g.hc; h += L) {  // unit 0: unaligned head
-      Key k;
-      bool valid, is_nan;
-      P::classify(src.elem<Elem>(g.begin + h), k, valid, is_nan);
-      x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, 0);
-    }
-    if (src.vec_staged) {
+    if constexpr (FAST) {
       staged_fold_vectors<P, L, true>(src, (uint32_t)g.nv, l, wi, x);
     } else {
-      staged_fold_vectors<P, L, false>(src, (uint32_t)g.nv, l, wi, x);
-    }
-    for (uint32_t q = l; q < g.tc; q += L) {  // unit nv+1: sub-vector tail
-      Key k;
-      bool valid, is_nan;
-      P::classify(src.elem<Elem>(g.a0 + g.nv * WindowGeom<P>::VE + q), k, valid, is_nan);
-      x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, (uint32_t)g.nv + 1);
+      for (uint32_t h = l; h < g.hc; h += L) {  // unit 0: unaligned head
+        Key k;
+        bool valid, is_nan;
+        P::classify(src.elem<Elem>(g.begin + h), k, valid, is_nan);
+        x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, 0);
+      }
+      if (src.vec_staged) {
+        staged_fold_vectors<P, L, true>(src, (uint32_t)g.nv, l, wi, x);
+      } else {
+        staged_fold_vectors<P, L, false>(src, (uint32_t)g.nv, l, wi, x);
+      }
+      for (uint32_t q = l; q < g.tc; q += L) {  // unit nv+1: sub-vector tail
+        Key k;
+        bool valid, is_nan;
+        P::classify(src.elem<Elem>(g.a0 + g.nv * WindowGeom<P>::VE + q), k, valid, is_nan);
+        x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, (uint32_t)g.nv + 1);
+      }
     }
     // ---- reduce inside the lane group (lexicographic on (key, unit))
 #pragma unroll
@@ -572,7 +613,7 @@ __global__ void __launch_bounds__(THREADS)
       const uint32_t unit = c == 0 ? x.umin : (c == 1 ? x.umax : x.unan);
       uint64_t r = POS_NONE;
       if (active && unit != 0xFFFFFFFFu && l == (uint32_t)(c % L))
-        r = staged_locate<P>(src, g, unit, c, c == 0 ? x.kmin : x.kmax);
+        r = staged_locate<P, FAST>(src, g, unit, c, c == 0 ? x.kmin : x.kmax);
       if (L > 1) r = __shfl_sync(0xFFFFFFFFu, r, (int)(lane - l) + (c % L));
       res[c] = r;
     }
@@ -588,11 +629,12 @@ __global__ void __launch_bounds__(THREADS)
         imin = res[0];
         imax = res[1];
       }
+      const uint64_t wo = p.w_first + w;  // p.out is indexed by the array's window id
       if (out16) {  // 16-byte store, coalesced over the windows of the block
-        reinterpret_cast<ulonglong2*>(p.out)[w] = make_ulonglong2(imin, imax);
+        reinterpret_cast<ulonglong2*>(p.out)[wo] = make_ulonglong2(imin, imax);
       } else {
-        p.out[2 * w] = imin;
-        p.out[2 * w + 1] = imax;
+        p.out[2 * wo] = imin;
+        p.out[2 * wo + 1] = imax;
       }
     }
     __syncthreads();  // everyone is done with stage s: it may be refilled
