@@ -54,6 +54,7 @@ struct amm_workspace {
   uint64_t launches;
   amm_host_pipeline* pipe;  // lazily created by amm_host_argminmax
   int win_staged;           // short windows take the TMA-staged kernel (AMM_WIN_STAGED=0: old path)
+  int win_staged_max;       // ... for windows up to this many bytes (mean)
   int win_lane_bytes;       // ... with one lane per this many bytes of window (1..8 lanes)
   int win_fast;             // geometry-free instantiation for aligned fixed windows (AMM_WIN_FAST=0: off)
   int win_chunked;          // few 1-64 MiB windows are cut into chunks (AMM_WIN_CHUNKED=0: off)

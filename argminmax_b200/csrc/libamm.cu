@@ -324,6 +324,7 @@ static int workspace_init(amm_workspace* ws, int device) {
   ws->win_staged = getenv("AMM_WIN_STAGED") ? atoi(getenv("AMM_WIN_STAGED")) : 1;
   ws->win_fast = getenv("AMM_WIN_FAST") ? atoi(getenv("AMM_WIN_FAST")) : 1;
   ws->win_chunked = getenv("AMM_WIN_CHUNKED") ? atoi(getenv("AMM_WIN_CHUNKED")) : 1;
+  ws->win_staged_max = getenv("AMM_WIN_STAGED_MAX") ? atoi(getenv("AMM_WIN_STAGED_MAX")) : 4096;
   ws->win_lane_bytes = getenv("AMM_WIN_LANE_BYTES") ? atoi(getenv("AMM_WIN_LANE_BYTES")) : 128;
   if (ws->win_lane_bytes < 16 || ws->win_lane_bytes > 1024) ws->win_lane_bytes = 128;
   ws->max_grid = ws->sm_count * 32;

@@ -160,7 +160,8 @@ static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cuda
 
 // Windowed form.  Regimes (B200 measurements, tools/windows_bench.py):
 //   <= 1 KB per window            TMA-staged blocks of windows, 1/2/4/8 lanes per window
-//   <= 2 KB per window            8 lanes per window (4 windows per warp), loads from global
+//   1 - 2 KB per window           8 lanes per window (4 windows per warp), loads from global
+//   2 - 4 KB per window           TMA-staged, one warp per window
 //   >= 4096 windows               one warp per window (enough warps to fill the machine)
 //   >= 4 x SMs windows            one 256-thread CTA per window, 16 KB in flight per CTA
 //   fewer                         one 512-thread CTA per window, 64 KB in flight per CTA
@@ -186,7 +187,7 @@ static int launch_windows_staged(amm_workspace* ws, const WindowParams& p, uint6
     if (n_full > 0) {
       WindowParams pf = p;
       pf.n_windows = n_full;
-      const uint64_t stage = WPB * p.window * ES;  // <= 128 x 128 B = 16 KiB by the dispatch rule
+      const uint64_t stage = WPB * p.window * ES;  // <= 128 lanes x 128 B = 16 KiB by the dispatch rule
       argminmax_windows_staged_kernel<P, L, THREADS, true>
           <<<grid_for(n_full), THREADS, (size_t)(2 * stage), stream>>>(pf, (uint32_t)stage);
       AMM_CUDA(cudaGetLastError());
@@ -225,11 +226,14 @@ static int launch_windows(amm_workspace* ws, const WindowParams& p, uint64_t mea
   }
   const uint64_t mean_bytes = mean_window * sizeof(typename P::Elem);
   const uint64_t lane_bytes = (uint64_t)ws->win_lane_bytes;  // target bytes per lane
-  if (mean_bytes <= 8 * lane_bytes && mean_bytes <= 1024 && ws->win_staged) {
+  // measured (tools/windows_bench.py): 8 lanes from global memory still win between 1 and 2 KB
+  if (ws->win_staged && mean_bytes <= (uint64_t)ws->win_staged_max &&
+      (mean_bytes <= 8 * lane_bytes || (mean_bytes > 16 * lane_bytes && mean_bytes <= 32 * lane_bytes))) {
     if (mean_bytes <= lane_bytes) return launch_windows_staged<P, 1>(ws, p, mean_bytes, stream);
     if (mean_bytes <= 2 * lane_bytes) return launch_windows_staged<P, 2>(ws, p, mean_bytes, stream);
     if (mean_bytes <= 4 * lane_bytes) return launch_windows_staged<P, 4>(ws, p, mean_bytes, stream);
-    return launch_windows_staged<P, 8>(ws, p, mean_bytes, stream);
+    if (mean_bytes <= 8 * lane_bytes) return launch_windows_staged<P, 8>(ws, p, mean_bytes, stream);
+    return launch_windows_staged<P, 32>(ws, p, mean_bytes, stream);
   }
   if (mean_window * sizeof(typename P::Elem) <= 2048) {
     grid = (p.n_windows + 31) / 32;

@@ -383,6 +383,10 @@ def main() -> int:
     # ---- small-n latency: us per call at 1M elements, synchronous C-ABI call timed inside the
     #      library (amm_measure_call_latency: host wall clock, no Python in the loop)
     import ctypes
+    # A B200 that has just streamed at full HBM rate answers small calls ~1.7 us slower for a few
+    # hundred ms (tools/exp/latency_after_load.py: 12.8 us right after 400 x 4 GiB scans, 11.0 us
+    # fresh and again 1 s later).  The probe measures the settled state a latency-bound caller sees.
+    time.sleep(1.0)
     lat3 = (ctypes.c_double * 3)()
     rc = amm.lib().amm_measure_call_latency(amm.DTYPES[DTYPE], data.data_ptr(), 1 << 20, amm.IGNORE_NAN,
                                             ws.handle, stream, 2000, lat3)
@@ -470,7 +474,8 @@ def main() -> int:
             "gpu_launches": int(launches), "us_per_call_1m": round(us_1m, 2),
             "us_per_call_1m_detail": {"median": round(lat3[0], 2), "min": round(lat3[1], 2), "p99": round(lat3[2], 2),
                                       "through_python_ctypes_median": round(us_1m_python, 2),
-                                      "what": "f32 n=2^20, synchronous amm_argminmax, host wall clock"},
+                                      "what": "f32 n=2^20, synchronous amm_argminmax, host wall clock, GPU idle for 1 s "
+                                              "before the probe (right after the streaming loops: +1.7 us)"},
             "result": list(result), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
