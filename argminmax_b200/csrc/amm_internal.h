@@ -41,6 +41,9 @@ struct amm_workspace {
   int direct_packed;      // 32-bit keys: packed-word atomics instead of partials (AMM_DIRECT_PACKED=0: off)
   int occupancy[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];      // cached CTAs/SM ...
   int occupancy_threads[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // ... for this CTA size
+  size_t static_smem[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];   // static smem of the kernel + 1 (0 = not queried)
+  size_t dyn_smem_set[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // MaxDynamicSharedMemorySize set so far
+  size_t smem_per_sm, smem_reserved_per_cta, smem_optin_per_cta;  // device limits (co-residency cap)
   void* partials;            // max_grid x 64 B
   uint32_t* ticket;          // last-block-done counter (self-resetting)
   amm_record* rec_dev;       // device record slot

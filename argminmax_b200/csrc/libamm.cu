@@ -299,6 +299,9 @@ static int workspace_init(amm_workspace* ws, int device) {
   cudaDeviceProp prop;
   AMM_CUDA(cudaGetDeviceProperties(&prop, device));
   ws->sm_count = prop.multiProcessorCount;
+  ws->smem_per_sm = prop.sharedMemPerMultiprocessor;
+  ws->smem_reserved_per_cta = prop.reservedSharedMemPerBlock;
+  ws->smem_optin_per_cta = prop.sharedMemPerBlockOptin;
   ws->threads = 0;      // automatic
   ws->ctas_per_sm = 0;  // automatic
   ws->variant = -1;     // automatic

@@ -515,75 +515,92 @@ constexpr unsigned long long PACK_MAX_NONE = 0ull;
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
   return __shfl_xor_sync(0xFFFFFFFFu, v, m);
 }
-template <class P>
-__device__ __forceinline__ void packed_finish(const ScanParams& p, const Best<int32_t>& x,
-                                              unsigned long long* smem /* [3][32] */,
-                                              uint32_t* s_is_last) {
-  unsigned long long wmin = PACK_MIN_NONE, wmax = PACK_MAX_NONE, wnan = POS_NONE;
-  if (x.pmin != POS_NONE)
-    wmin = ((unsigned long long)((uint32_t)x.kmin ^ 0x80000000u) << 32) | (uint32_t)x.pmin;
-  if (x.pmax != POS_NONE)
-    wmax = ((unsigned long long)((uint32_t)x.kmax ^ 0x80000000u) << 32) | (uint32_t)~(uint32_t)x.pmax;
-  if (P::TRACK_NAN) wnan = x.pnan;
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const unsigned long long a = shfl_xor_u64(wmin, m), b = shfl_xor_u64(wmax, m);
-    wmin = a < wmin ? a : wmin;
-    wmax = b > wmax ? b : wmax;
-    if (P::TRACK_NAN) {
-      const unsigned long long c = shfl_xor_u64(wnan, m);
-      wnan = c < wnan ? c : wnan;
-    }
+struct PackedWords {
+  unsigned long long wmin, wmax, wnan;
+  __device__ __forceinline__ void clear() {
+    wmin = PACK_MIN_NONE;
+    wmax = PACK_MAX_NONE;
+    wnan = POS_NONE;
   }
+  __device__ __forceinline__ void set_min(int32_t key, uint32_t pos) {
+    wmin = ((unsigned long long)((uint32_t)key ^ 0x80000000u) << 32) | pos;
+  }
+  __device__ __forceinline__ void set_max(int32_t key, uint32_t pos) {
+    wmax = ((unsigned long long)((uint32_t)key ^ 0x80000000u) << 32) | (uint32_t)~pos;
+  }
+  // -> Best with 32-bit positions widened
+  __device__ __forceinline__ Best<int32_t> unpack() const {
+    Best<int32_t> g;
+    g.clear();
+    if (wmin != PACK_MIN_NONE) {
+      g.kmin = (int32_t)((uint32_t)(wmin >> 32) ^ 0x80000000u);
+      g.pmin = (uint32_t)wmin;
+    }
+    if (wmax != PACK_MAX_NONE) {
+      g.kmax = (int32_t)((uint32_t)(wmax >> 32) ^ 0x80000000u);
+      g.pmax = (uint32_t)~(uint32_t)wmax;
+    }
+    g.pnan = wnan;
+    return g;
+  }
+};
+
+// Folds every thread's words over the CTA and then over the grid.  Returns true in ALL lanes of
+// warp 0 of the last CTA to arrive (or of the only CTA), with the grid-wide words in `w`; every
+// other thread gets false.  All threads of the CTA must call (one __syncthreads inside).
+template <class P>
+__device__ __forceinline__ bool packed_grid_reduce(const ScanParams& p, PackedWords& w,
+                                                   unsigned long long* smem /* [3][32] */) {
+  auto warp_fold = [&]() {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      const unsigned long long a = shfl_xor_u64(w.wmin, m), b = shfl_xor_u64(w.wmax, m);
+      w.wmin = a < w.wmin ? a : w.wmin;
+      w.wmax = b > w.wmax ? b : w.wmax;
+      if (P::TRACK_NAN) {
+        const unsigned long long c = shfl_xor_u64(w.wnan, m);
+        w.wnan = c < w.wnan ? c : w.wnan;
+      }
+    }
+  };
+  warp_fold();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = (blockDim.x + 31) >> 5;
   if (lane == 0) {
-    smem[warp] = wmin;
-    smem[32 + warp] = wmax;
-    if (P::TRACK_NAN) smem[64 + warp] = wnan;
+    smem[warp] = w.wmin;
+    smem[32 + warp] = w.wmax;
+    if (P::TRACK_NAN) smem[64 + warp] = w.wnan;
   }
   __syncthreads();
-  if (warp != 0) return;
-  wmin = lane < nwarps ? smem[lane] : PACK_MIN_NONE;
-  wmax = lane < nwarps ? smem[32 + lane] : PACK_MAX_NONE;
-  if (P::TRACK_NAN) wnan = lane < nwarps ? smem[64 + lane] : POS_NONE;
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) {
-    const unsigned long long a = shfl_xor_u64(wmin, m), b = shfl_xor_u64(wmax, m);
-    wmin = a < wmin ? a : wmin;
-    wmax = b > wmax ? b : wmax;
-    if (P::TRACK_NAN) {
-      const unsigned long long c = shfl_xor_u64(wnan, m);
-      wnan = c < wnan ? c : wnan;
+  if (warp != 0) return false;
+  w.wmin = lane < nwarps ? smem[lane] : PACK_MIN_NONE;
+  w.wmax = lane < nwarps ? smem[32 + lane] : PACK_MAX_NONE;
+  w.wnan = (P::TRACK_NAN && lane < nwarps) ? smem[64 + lane] : POS_NONE;
+  warp_fold();
+  uint32_t last = 1;
+  if (lane == 0) {
+    pdl_wait_prior_grid();  // from here on the workspace is ours
+    if (gridDim.x > 1) {
+      unsigned long long* words = reinterpret_cast<unsigned long long*>(p.ticket + 16);
+      if (w.wmin != PACK_MIN_NONE) atomicMin(&words[0], w.wmin);
+      if (w.wmax != PACK_MAX_NONE) atomicMax(&words[1], w.wmax);
+      if (P::TRACK_NAN && w.wnan != POS_NONE) atomicMin(&words[2], w.wnan);
+      __threadfence();
+      last = atomicInc(p.ticket, gridDim.x - 1) == gridDim.x - 1;
+      if (last) {
+        __threadfence();
+        w.wmin = atomicExch(&words[0], PACK_MIN_NONE);  // read the grid-wide result and re-arm
+        w.wmax = atomicExch(&words[1], PACK_MAX_NONE);
+        if (P::TRACK_NAN) w.wnan = atomicExch(&words[2], POS_NONE);
+      }
     }
   }
-  if (lane != 0) return;
-  pdl_wait_prior_grid();  // from here on the workspace is ours
-  unsigned long long* words = reinterpret_cast<unsigned long long*>(p.ticket + 16);
-  if (gridDim.x > 1) {
-    if (wmin != PACK_MIN_NONE) atomicMin(&words[0], wmin);
-    if (wmax != PACK_MAX_NONE) atomicMax(&words[1], wmax);
-    if (P::TRACK_NAN && wnan != POS_NONE) atomicMin(&words[2], wnan);
-    __threadfence();
-    if (atomicInc(p.ticket, gridDim.x - 1) != gridDim.x - 1) return;
-    __threadfence();
-    wmin = atomicExch(&words[0], PACK_MIN_NONE);  // read the grid-wide result and re-arm
-    wmax = atomicExch(&words[1], PACK_MAX_NONE);
-    if (P::TRACK_NAN) wnan = atomicExch(&words[2], POS_NONE);
-  }
-  Best<int32_t> g;
-  g.clear();
-  if (wmin != PACK_MIN_NONE) {
-    g.kmin = (int32_t)((uint32_t)(wmin >> 32) ^ 0x80000000u);
-    g.pmin = (uint32_t)wmin;
-  }
-  if (wmax != PACK_MAX_NONE) {
-    g.kmax = (int32_t)((uint32_t)(wmax >> 32) ^ 0x80000000u);
-    g.pmax = (uint32_t)~(uint32_t)wmax;
-  }
-  if (P::TRACK_NAN) g.pnan = wnan;
-  publish_record(p, make_record(p, g));
-  (void)s_is_last;
+  last = __shfl_sync(0xFFFFFFFFu, last, 0);
+  if (!last) return false;
+  w.wmin = __shfl_sync(0xFFFFFFFFu, w.wmin, 0);
+  w.wmax = __shfl_sync(0xFFFFFFFFu, w.wmax, 0);
+  w.wnan = __shfl_sync(0xFFFFFFFFu, w.wnan, 0);
+  return true;
 }
 
 template <class P, bool XCHG, bool PACKED = false>
@@ -643,7 +660,13 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
   if (blockIdx.x == gridDim.x - 1) exact_range<P, false>(bd, p.base, p.tail_start, p.n, x);
   if constexpr (PACKED) {
     static_assert(sizeof(Key) == 4 && !XCHG, "packed candidates need 32-bit keys");
-    packed_finish<P>(p, x, reinterpret_cast<unsigned long long*>(smem), &s_is_last);
+    PackedWords w;
+    w.clear();
+    if (x.pmin != POS_NONE) w.set_min(x.kmin, (uint32_t)x.pmin);
+    if (x.pmax != POS_NONE) w.set_max(x.kmax, (uint32_t)x.pmax);
+    if (P::TRACK_NAN) w.wnan = x.pnan;
+    if (!packed_grid_reduce<P>(p, w, reinterpret_cast<unsigned long long*>(smem))) return;
+    if (threadIdx.x == 0) publish_record(p, make_record(p, w.unpack()));
   } else {
     x = block_reduce(x, smem);
     if (!grid_reduce(p, x, smem, &s_is_last)) return;

@@ -29,12 +29,12 @@ constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 // Launch with the programmatic-stream-serialization attribute (see pdl_* in scan_kernel.cuh).
 template <typename Kernel>
 static cudaError_t launch_scan(Kernel kernel, unsigned grid, unsigned threads, cudaStream_t stream,
-                               const ScanParams& p, bool pdl) {
+                               const ScanParams& p, bool pdl, size_t dyn_smem = 0) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = dyn_smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr;
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -76,7 +76,34 @@ static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int vari
   if (grid > tiles) grid = tiles;
   if (grid < 1) grid = 1;
   if (grid > (uint64_t)ws->max_grid) grid = (uint64_t)ws->max_grid;
-  AMM_CUDA(launch_scan(kernel, (unsigned)grid, (unsigned)threads, stream, p, ws->pdl != 0));
+  // With programmatic dependent launch the CTAs of the NEXT scan on the stream become resident
+  // while this one runs.  If an SM can hold more than twice the CTAs a scan puts on it, the
+  // block scheduler packs the next grid onto the free slots of fewer SMs (3 per SM instead of
+  // 2) and that scan then streams from part of the GPU only (measured with a 47-register
+  // build of this kernel and 2 CTAs per SM: +10-20 us on a 200 MB scan).  Unused dynamic shared
+  // memory caps the co-residency at exactly 2 x per_sm CTAs per SM.  Not in pipelined mode,
+  // where consecutive scans stream concurrently and extra resident CTAs help.
+  size_t dyn = 0;
+  if (ws->pdl && !p.pipelined && occ > 2 * per_sm && ws->smem_per_sm > 0) {
+    size_t& stat = ws->static_smem[dtype_slot][vslot];
+    if (stat == 0) {
+      cudaFuncAttributes fa;
+      AMM_CUDA(cudaFuncGetAttributes(&fa, kernel));
+      stat = fa.sharedSizeBytes + 1;  // +1: "queried" marker for kernels without static smem
+    }
+    const size_t per_cta = ws->smem_per_sm / (size_t)(2 * per_sm);
+    const size_t fixed = (stat - 1) + ws->smem_reserved_per_cta;
+    if (per_cta > fixed + 1024) {
+      dyn = (per_cta - fixed) / 128 * 128;
+      if (dyn > ws->smem_optin_per_cta - (stat - 1)) dyn = (ws->smem_optin_per_cta - (stat - 1)) / 128 * 128;
+      size_t& have = ws->dyn_smem_set[dtype_slot][vslot];
+      if (have < dyn) {
+        AMM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        have = dyn;
+      }
+    }
+  }
+  AMM_CUDA(launch_scan(kernel, (unsigned)grid, (unsigned)threads, stream, p, ws->pdl != 0, dyn));
   ws->last_grid = (int)grid;
   ws->last_threads = threads;
   ws->launches += 1;

@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""A/B of the big-input scan's tile schedule (static grid-stride vs dynamic claims) inside ONE
+"""NEEDS tools/exp/dynamic_tile_claims.patch applied (it adds amm_workspace_set_dynamic): the
+product keeps the static schedule, see profiles/r01d_schedule_experiment.md.
+
+A/B of the big-input scan's tile schedule (static grid-stride vs dynamic claims) inside ONE
 process on the SAME buffers, interleaved in short blocks so that box / allocation / thermal
 differences cancel.  Prints one JSON line per (buffer, schedule, mode) with the per-block
 GB/s samples.  Usage: python tools/exp/dyn_ab.py [--blocks 8] [--launches 50] [--buffers 2]"""
