@@ -212,3 +212,48 @@ def test_few_large_windows_are_chunked(dt):
             assert [tuple(r) for r in ds.argminmax_windows(window, mode).cpu().tolist()] == exp_fixed
             assert [tuple(r) for r in ds.argminmax_windows(offs, mode).cpu().tolist()] == exp_ragged
     plain.close()
+
+
+@pytest.mark.parametrize("dt", G.ALL_DTYPES)
+def test_fuzz_windows(dt):
+    """Seeded fuzz over the windowed form: random length, base alignment, window shape (fixed
+    of any size, ragged with empty windows and outliers), NaN / +-inf / type extremes sprinkled
+    in, many ties.  Every window must equal the oracle on its sub-slice, whatever kernel the
+    dispatcher picks (staged 1..32 lanes incl. the geometry-free form, 8 lanes from global, warp,
+    CTA, chunked)."""
+    import torch
+    rng = np.random.default_rng(7000 + G.ALL_DTYPES.index(dt))
+    T = G.NP[dt]
+    es = np.dtype(T).itemsize
+    for _case in range(24):
+        n = int(rng.integers(1, 400_000)) if rng.random() < 0.8 else int(rng.integers(1, 300))
+        a = random_array(dt, n, rng) if rng.random() < 0.5 else rng.integers(0, 4, n).astype(T)
+        if dt in G.FLOAT_DTYPES:
+            k = int(rng.integers(0, max(2, n // 40)))
+            a[rng.integers(0, n, k)] = rng.choice(np.array([np.nan, np.inf, -np.inf, 0.0], dtype=T), k)
+            if rng.random() < 0.3 and n > 100:
+                s0 = int(rng.integers(0, n - 50))
+                a[s0:s0 + int(rng.integers(1, 3000))] = np.nan       # NaN runs spanning windows
+        off = int(rng.integers(0, 32 // es)) * es
+        ds, _keep = to_device(a, byte_offset=off)
+        if rng.random() < 0.6:
+            window = int(rng.choice([1, 2, 3, 4, 8, 16, 33, 64, 100, 128, 250, 256, 1000, 1024, 5000,
+                                     70_000, n, n + 5]))
+            if window == 1 and n > 50_000:
+                window = 2
+            nwin = -(-n // window)
+            bounds = [(w * window, min(n, (w + 1) * window)) for w in range(nwin)]
+            arg = window
+        else:
+            mean = int(rng.choice([3, 20, 100, 700, 5000]))
+            nwin = max(1, min(n // mean, 20_000))
+            cuts = np.sort(rng.integers(0, n + 1, nwin + 1))
+            cuts[0] = 0 if rng.random() < 0.5 else cuts[0]
+            if rng.random() < 0.3 and nwin > 4:      # an outlier: one window swallows a big range
+                cuts[nwin // 2:] = np.maximum(cuts[nwin // 2:], min(n, cuts[nwin // 2 - 1] + n // 3))
+            bounds = list(zip(cuts[:-1].tolist(), cuts[1:].tolist()))
+            arg = torch.from_numpy(cuts.astype(np.int64)).cuda()
+        for mode in modes_for(dt):
+            got = [tuple(r) for r in ds.argminmax_windows(arg, mode).cpu().tolist()]
+            assert got == _expected(a, bounds, mode), (dt, _case, n, off, mode,
+                                                       arg if isinstance(arg, int) else "ragged")
