@@ -257,3 +257,18 @@ def test_fuzz_windows(dt):
             got = [tuple(r) for r in ds.argminmax_windows(arg, mode).cpu().tolist()]
             assert got == _expected(a, bounds, mode), (dt, _case, n, off, mode,
                                                        arg if isinstance(arg, int) else "ragged")
+
+
+def test_large_mean_but_all_windows_empty():
+    """Few windows over a big array whose offsets all collapse to one point: every window is
+    empty -> (-1, -1) pairs (the chunked path has nothing to cut and must hand over)."""
+    import torch
+    a = np.arange(8_000_000, dtype=np.float32)
+    ds, _keep = to_device(a)
+    for point in (0, 4_000_000, a.size):
+        offs = torch.full((5,), point, dtype=torch.int64, device="cuda:0")
+        got = [tuple(r) for r in ds.argminmax_windows(offs, 0).cpu().tolist()]
+        assert got == [(-1, -1)] * 4
+    offs = torch.tensor([0, 0, a.size, a.size], dtype=torch.int64, device="cuda:0")
+    got = [tuple(r) for r in ds.argminmax_windows(offs, 0).cpu().tolist()]
+    assert got == [(-1, -1), (0, a.size - 1), (-1, -1)]
