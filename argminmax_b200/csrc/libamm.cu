@@ -326,8 +326,8 @@ static int workspace_init(amm_workspace* ws, int device) {
   ws->pdl = getenv("AMM_PDL") ? atoi(getenv("AMM_PDL")) : 1;
   ws->win_staged = getenv("AMM_WIN_STAGED") ? atoi(getenv("AMM_WIN_STAGED")) : 1;
   ws->win_fast = getenv("AMM_WIN_FAST") ? atoi(getenv("AMM_WIN_FAST")) : 1;
-  ws->win_chunks_per_sm = getenv("AMM_WIN_CHUNKS_PER_SM") ? atoi(getenv("AMM_WIN_CHUNKS_PER_SM")) : 32;
-  if (ws->win_chunks_per_sm < 4 || ws->win_chunks_per_sm > 256) ws->win_chunks_per_sm = 32;
+  ws->win_chunks_per_sm = getenv("AMM_WIN_CHUNKS_PER_SM") ? atoi(getenv("AMM_WIN_CHUNKS_PER_SM")) : 16;
+  if (ws->win_chunks_per_sm < 4 || ws->win_chunks_per_sm > 256) ws->win_chunks_per_sm = 16;
   ws->win_chunked = getenv("AMM_WIN_CHUNKED") ? atoi(getenv("AMM_WIN_CHUNKED")) : 1;
   ws->win_staged_max = getenv("AMM_WIN_STAGED_MAX") ? atoi(getenv("AMM_WIN_STAGED_MAX")) : 4096;
   ws->win_lane_bytes = getenv("AMM_WIN_LANE_BYTES") ? atoi(getenv("AMM_WIN_LANE_BYTES")) : 128;
@@ -687,7 +687,7 @@ static int host_window_bounds(const uint64_t* dev_offsets, uint64_t n, uint64_t 
 
 // Few LARGE windows (1 MiB ... 64 MiB each, fewer than 4 per SM): one CTA per window would
 // leave most of the GPU idle and one streaming scan per window pays ~6 us each.  Instead every
-// window is cut into equal chunks (>= 128 KiB, about 32 per SM), the chunks run through the
+// window is cut into equal chunks (>= 128 KiB, about 16 per SM), the chunks run through the
 // ordinary windowed kernels as if they were windows -- thousands of them, so the whole GPU
 // streams -- and a combine kernel folds each window's chunk answers (first occurrence: the
 // lowest chunk wins ties).  One extra launch, < 1 % extra traffic.
@@ -700,10 +700,11 @@ static int windows_chunked(int dtype, int slot, const void* dev_ptr, uint64_t n,
   if (rc) return rc;
   for (uint64_t w = 1; w < n_windows; ++w)
     if (begins[w] != ends[w - 1]) return kNotApplicable;  // not adjacent: caller falls back
-  // Aim at ~32 equal chunks per SM (>= 128 KiB each): enough of them that the hardware block
-  // scheduler balances the tail, large enough that the per-chunk reduce + locate stays < 2 %.
-  // Measured on 1 GiB (AMM_WIN_CHUNKS_PER_SM = 4 / 8 / 16 / 32): f32 54 x 20 MB windows
-  // 5.1 / 6.0 / 5.8 / 5.9 TB/s, 269 x 4 MB 4.9 / 5.6 / 5.9 / 5.9, u8 68 x 16 MB 4.8 / 5.8 / 5.8 / 5.9.
+  // Aim at ~16 equal chunks per SM (>= 128 KiB each, ~2400 in all): they run one per 256-thread
+  // CTA and the hardware block scheduler balances the tail; the per-chunk reduce + locate stays
+  // below 2 %.  Measured on 1 GiB with 4 / 8 / 16 / 32 / 64 chunks per SM: f32 269 x 4 MB windows
+  // 4.9 / 5.6 / 5.9 / 5.9 / 5.4 TB/s, f64 135 x 8 MB -- / -- / 5.8 / 5.1 / 5.4 (at 32 the chunks
+  // outnumber 4096 and go one per WARP, which for 8-byte dtypes is 1.4 resident rounds).
   const uint64_t slots = (uint64_t)ws->sm_count * (uint64_t)ws->win_chunks_per_sm;
   const uint64_t span = ends[n_windows - 1] - begins[0];
   uint64_t chunk = (span + (slots - n_windows) - 1) / (slots - n_windows);  // elements per chunk

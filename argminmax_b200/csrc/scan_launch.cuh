@@ -243,6 +243,8 @@ static int launch_windows(amm_workspace* ws, const WindowParams& p, uint64_t mea
                           cudaStream_t stream) {
   const uint64_t cap = (uint64_t)ws->sm_count * 8;
   uint64_t grid;
+  // vector unit of the warp- / CTA-per-window kernels: 32 bytes for 8-byte dtypes
+  constexpr int WVEC = sizeof(typename P::Elem) == 8 ? 32 : 16;
   if (p.chunk_first != nullptr) {  // combine step of the chunked form
     grid = (p.n_windows + 7) / 8;
     grid = grid > cap ? cap : (grid < 1 ? 1 : grid);
@@ -269,14 +271,14 @@ static int launch_windows(amm_workspace* ws, const WindowParams& p, uint64_t mea
   } else if (p.n_windows >= 4096) {
     grid = (p.n_windows + 7) / 8;  // 8 warps per CTA, one window per warp
     grid = grid > cap ? cap : (grid < 1 ? 1 : grid);
-    argminmax_windows_warp_kernel<P, 32><<<(unsigned)grid, 256, 0, stream>>>(p);
+    argminmax_windows_warp_kernel<P, 32, WVEC><<<(unsigned)grid, 256, 0, stream>>>(p);
   } else if (p.n_windows >= (uint64_t)ws->sm_count * 4) {
     grid = p.n_windows < cap ? p.n_windows : cap;
-    argminmax_windows_cta_kernel<P, 256, 4><<<(unsigned)grid, 256, 0, stream>>>(p);
+    argminmax_windows_cta_kernel<P, 256, 4, WVEC><<<(unsigned)grid, 256, 0, stream>>>(p);
   } else {
     grid = p.n_windows < cap ? p.n_windows : cap;
     grid = grid < 1 ? 1 : grid;
-    argminmax_windows_cta_kernel<P, 512, 8><<<(unsigned)grid, 512, 0, stream>>>(p);
+    argminmax_windows_cta_kernel<P, 512, (WVEC == 32 ? 4 : 8), WVEC><<<(unsigned)grid, 512, 0, stream>>>(p);
   }
   AMM_CUDA(cudaGetLastError());
   ws->launches += 1;

@@ -55,11 +55,14 @@ __device__ __forceinline__ void window_bounds(const WindowParams& p, uint64_t w,
 // per element is that of the streaming kernel; the per-window overhead is one reduce + three
 // single-element loads.
 // ---------------------------------------------------------------------------------------
-template <class P>
+// VECB = bytes per vector unit: 16 everywhere except the warp- / CTA-per-window kernels on 8-byte
+// dtypes, which use 32-byte vectors (the sm_100 256-bit load) so that the per-unit bookkeeping --
+// ~35 instructions with 64-bit keys -- is paid per four elements instead of per two.
+template <class P, int VECB = 16>
 struct WindowGeom {
-  static constexpr uint32_t VE = 16 / sizeof(typename P::Elem);
+  static constexpr uint32_t VE = VECB / sizeof(typename P::Elem);
   uint64_t begin, end;  // elements
-  uint64_t a0;          // first element of unit 1 (16-byte aligned address)
+  uint64_t a0;          // first element of unit 1 (VECB-aligned address)
   uint32_t hc, tc;      // head / tail element counts (< VE)
   uint64_t nv;          // aligned vectors
   // a window that is exactly `vecs` aligned 16-byte vectors: no head, no tail
@@ -68,7 +71,7 @@ struct WindowGeom {
   __device__ __forceinline__ WindowGeom(const uint8_t* base, uint64_t b, uint64_t e)
       : begin(b), end(e) {
     const uint64_t addr = (uint64_t)(uintptr_t)base + b * sizeof(typename P::Elem);
-    uint64_t head = ((16 - (addr & 15)) & 15) / sizeof(typename P::Elem);
+    uint64_t head = ((VECB - (addr & (VECB - 1))) & (VECB - 1)) / sizeof(typename P::Elem);
     const uint64_t len = e - b;
     head = head < len ? head : len;
     hc = (uint32_t)head;
@@ -92,9 +95,10 @@ struct WindowGeom {
 };
 
 // value-only fold of this thread's share of the window; units are visited in ascending order
-template <class P, int STRIDE, int UN = 4>
-__device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeom<P>& g,
+template <class P, int STRIDE, int UN = 4, int VECB = 16>
+__device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeom<P, VECB>& g,
                                             uint32_t t, Best<typename P::Key>& x) {
+  constexpr int NW = VECB / 4;
   using Elem = typename P::Elem;
   using Key = typename P::Key;
   const Elem* e = reinterpret_cast<const Elem*>(base);
@@ -117,11 +121,11 @@ __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeo
   }
   const uint8_t* vbase = base + g.a0 * sizeof(Elem);
   for (uint64_t v0 = t; v0 < g.nv; v0 += (uint64_t)UN * STRIDE) {
-    uint32_t w[UN][4];
+    uint32_t w[UN][NW];
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const uint64_t v = v0 + (uint64_t)u * STRIDE;
-      if (v < g.nv) VecLoad<16>::ld(vbase + v * 16, w[u]);
+      if (v < g.nv) VecLoad<VECB>::ld(vbase + v * VECB, w[u]);
     }
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
@@ -130,7 +134,7 @@ __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeo
         typename P::Acc acc;
         P::init(acc, &w[u][0]);
 #pragma unroll
-        for (int q = P::WPI; q < 4; q += P::WPI) P::feed(acc, &w[u][q]);
+        for (int q = P::WPI; q < NW; q += P::WPI) P::feed(acc, &w[u][q]);
         Key kmin, kmax;
         bool valid, has_nan;
         P::finish(acc, kmin, kmax, valid, has_nan);
@@ -141,7 +145,7 @@ __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeo
   for (uint32_t q = t; q < g.tc; q += STRIDE) {  // unit nv+1: the tail
     Key k;
     bool valid, is_nan;
-    P::classify(e[g.a0 + g.nv * WindowGeom<P>::VE + q], k, valid, is_nan);
+    P::classify(e[g.a0 + g.nv * WindowGeom<P, VECB>::VE + q], k, valid, is_nan);
     consider(k, k, valid, P::TRACK_NAN && is_nan, g.nv + 1);
   }
 }
@@ -150,9 +154,9 @@ __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeo
 // hundred bytes) re-reads the winning units, G elements per step, and a ballot picks the first
 // match; lane 0 of the group writes the window's answer.  Every lane of the warp executes
 // the same ballots (inactive groups contribute no hits).
-template <class P, int G>
+template <class P, int G, int VECB = 16>
 __device__ __forceinline__ void window_locate_store(const WindowParams& p, uint64_t w, bool active,
-                                                    const WindowGeom<P>& g,
+                                                    const WindowGeom<P, VECB>& g,
                                                     const Best<typename P::Key>& x, uint32_t lane) {
   using Elem = typename P::Elem;
   using Key = typename P::Key;
@@ -166,7 +170,7 @@ __device__ __forceinline__ void window_locate_store(const WindowParams& p, uint6
     uint64_t first = 0;
     uint32_t count = 0;
     if (active && units[c] != POS_NONE) g.unit_range(units[c], first, count);
-    constexpr uint32_t STEPS = (WindowGeom<P>::VE + G - 1) / G;  // units hold <= VE elements
+    constexpr uint32_t STEPS = (WindowGeom<P, VECB>::VE + G - 1) / G;  // units hold <= VE elements
 #pragma unroll
     for (uint32_t st = 0; st < STEPS; ++st) {
       const uint32_t k_in_unit = st * G + sl;
@@ -233,7 +237,7 @@ __device__ __forceinline__ void window_group_reduce(Best<typename P::Key>& x) {
 }
 
 // one group of G lanes per window (32 / G windows per warp), grid-stride over windows
-template <class P, int G>
+template <class P, int G, int VECB = 16>
 __global__ void __launch_bounds__(256) argminmax_windows_warp_kernel(const WindowParams p) {
   using Key = typename P::Key;
   constexpr uint32_t PER_WARP = 32 / G;
@@ -246,12 +250,12 @@ __global__ void __launch_bounds__(256) argminmax_windows_warp_kernel(const Windo
     const bool active = w < p.n_windows;
     uint64_t begin = 0, end = 0;
     if (active) window_bounds<P>(p, w, begin, end);
-    const WindowGeom<P> g(p.base, begin, end);
+    const WindowGeom<P, VECB> g(p.base, begin, end);
     Best<Key> x;
     x.clear();
-    window_fold<P, G>(p.base, g, lane % G, x);
+    window_fold<P, G, 4, VECB>(p.base, g, lane % G, x);
     window_group_reduce<P, G>(x);
-    window_locate_store<P, G>(p, w, active, g, x, lane);
+    window_locate_store<P, G, VECB>(p, w, active, g, x, lane);
   }
 }
 
@@ -692,19 +696,19 @@ __global__ void __launch_bounds__(256) argminmax_windows_combine_kernel(const Wi
 }
 
 // one CTA per window (large windows)
-template <class P, int THREADS, int UN>
+template <class P, int THREADS, int UN, int VECB = 16>
 __global__ void __launch_bounds__(THREADS) argminmax_windows_cta_kernel(const WindowParams p) {
   using Key = typename P::Key;
   __shared__ Best<Key> smem[32];
   for (uint64_t w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
     uint64_t begin, end;
     window_bounds<P>(p, w, begin, end);
-    const WindowGeom<P> g(p.base, begin, end);
+    const WindowGeom<P, VECB> g(p.base, begin, end);
     Best<Key> x;
     x.clear();
-    window_fold<P, THREADS, UN>(p.base, g, threadIdx.x, x);  // THREADS * UN * 16 B in flight
+    window_fold<P, THREADS, UN, VECB>(p.base, g, threadIdx.x, x);  // THREADS * UN * VECB bytes in flight
     x = block_reduce(x, smem);
-    if (threadIdx.x < 32) window_locate_store<P, 32>(p, w, true, g, x, threadIdx.x);
+    if (threadIdx.x < 32) window_locate_store<P, 32, VECB>(p, w, true, g, x, threadIdx.x);
   }
 }
 
