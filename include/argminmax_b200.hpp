@@ -103,6 +103,28 @@ class DeviceSlice {
   template <typename U = T, typename = std::enable_if_t<dtype_of<U>::is_float>>
   size_t nanargmax() const { return run(AMM_RETURN_NAN).second; }
 
+  // Widened row (not part of the reference's traits): what a down-sampler gets by
+  // calling argminmax() once per bin -- (argmin, argmax) of every consecutive window of `window`
+  // elements (the last may be shorter), absolute indices, ONE launch.  Blocking; default-stream
+  // slices only (the result is copied back with the C ABI's synchronous copy).
+  std::vector<std::pair<size_t, size_t>> argminmax_windows(size_t window, int mode = AMM_IGNORE_NAN) const {
+    if (stream_ != nullptr) throw Error(AMM_ERR_ARG, "argminmax_windows: default-stream slices only");
+    if (window == 0) throw Error(AMM_ERR_ARG, "argminmax_windows: window == 0");
+    const size_t nwin = (n_ + window - 1) / window;
+    std::vector<std::pair<size_t, size_t>> res(nwin);
+    if (nwin == 0) check(AMM_ERR_EMPTY, "amm_argminmax_fixed_windows");
+    void* d_out = nullptr;
+    check(amm_device_alloc(ws_->device(), nwin * 2 * sizeof(uint64_t), &d_out), "amm_device_alloc");
+    std::vector<uint64_t> h(2 * nwin);
+    const int rc = amm_argminmax_fixed_windows(dtype_of<T>::code, ptr_, n_, window, mode, ws_->get(),
+                                               nullptr, static_cast<uint64_t*>(d_out));
+    const int rc2 = rc ? rc : amm_copy_to_host(ws_->device(), h.data(), d_out, h.size() * sizeof(uint64_t));
+    amm_device_free(ws_->device(), d_out);
+    check(rc2, "amm_argminmax_fixed_windows");
+    for (size_t w = 0; w < nwin; ++w) res[w] = {static_cast<size_t>(h[2 * w]), static_cast<size_t>(h[2 * w + 1])};
+    return res;
+  }
+
  private:
   std::pair<size_t, size_t> run(int mode) const {
     uint64_t out[2];

@@ -57,6 +57,17 @@ extern "C" {
         mode: c_int,
         out: *mut u64,
     ) -> c_int;
+    fn amm_argminmax_fixed_windows(
+        dtype: c_int,
+        dev_ptr: *const c_void,
+        n: u64,
+        window: u64,
+        mode: c_int,
+        ws: *mut AmmWorkspace,
+        stream: *mut c_void,
+        dev_out: *mut u64,
+    ) -> c_int;
+    fn amm_copy_to_host(device: c_int, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
     fn amm_device_alloc(device: c_int, bytes: usize, dev_ptr: *mut *mut c_void) -> c_int;
     fn amm_device_free(device: c_int, dev_ptr: *mut c_void) -> c_int;
     fn amm_copy_to_device(device: c_int, dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
@@ -134,6 +145,30 @@ impl<'w, T: CudaDType> DeviceSlice<'w, T> {
     }
     pub fn is_empty(&self) -> bool {
         self.len == 0
+    }
+    /// Not part of the reference's traits: what a down-sampler gets by calling
+    /// `argminmax()` once per bin -- `(argmin, argmax)` of every consecutive window of `window`
+    /// elements (the last may be shorter), absolute indices, in ONE launch.  `return_nan`
+    /// selects the `NaNArgMinMax` semantics per window.
+    pub fn argminmax_windows(&self, window: usize, return_nan: bool) -> Vec<(usize, usize)> {
+        assert!(window > 0 && self.len > 0); // the reference panics on empty input as well
+        let nwin = (self.len + window - 1) / window;
+        let bytes = nwin * 2 * std::mem::size_of::<u64>();
+        let mut d: *mut c_void = std::ptr::null_mut();
+        check(unsafe { amm_device_alloc(self.ws.device, bytes, &mut d) }, "amm_device_alloc");
+        let mode = if return_nan { AMM_RETURN_NAN } else { AMM_IGNORE_NAN };
+        let rc = unsafe {
+            amm_argminmax_fixed_windows(T::CODE, self.ptr as *const c_void, self.len as u64,
+                                        window as u64, mode, self.ws.raw, std::ptr::null_mut(),
+                                        d as *mut u64)
+        };
+        let mut host = vec![0u64; 2 * nwin];
+        let rc2 = if rc != 0 { rc } else {
+            unsafe { amm_copy_to_host(self.ws.device, host.as_mut_ptr() as *mut c_void, d, bytes) }
+        };
+        unsafe { amm_device_free(self.ws.device, d) };
+        check(rc2, "amm_argminmax_fixed_windows");
+        host.chunks_exact(2).map(|p| (p[0] as usize, p[1] as usize)).collect()
     }
     fn run(&self, mode: c_int) -> (usize, usize) {
         let mut out = [0u64; 2];

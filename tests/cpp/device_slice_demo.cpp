@@ -96,6 +96,27 @@ static int run_checks() {
     if (!threw) return 1;
     ++g_checks;
   }
+  {  // widened row: one launch for many bins == argminmax() per bin (MinMax down-sampling)
+    std::vector<float> v(100003);
+    for (size_t i = 0; i < v.size(); ++i) v[i] = std::sin(0.37f * (float)i) + 1e-3f * (float)(i % 97);
+    auto d = DeviceSlice<float>::from_host(v.data(), v.size(), ws);
+    for (size_t window : {64u, 1000u, 30000u}) {
+      const auto got = d.argminmax_windows(window);
+      for (size_t w = 0; w < got.size(); ++w) {
+        const size_t b = w * window, e = std::min(v.size(), b + window);
+        size_t imin = b, imax = b;
+        for (size_t i = b; i < e; ++i) {  // first occurrence, strict compares
+          if (v[i] < v[imin]) imin = i;
+          if (v[i] > v[imax]) imax = i;
+        }
+        if (got[w].first != imin || got[w].second != imax) {
+          std::fprintf(stderr, "FAIL windows(%zu) bin %zu\n", window, w);
+          return 1;
+        }
+      }
+      ++g_checks;
+    }
+  }
   std::printf("OK %d\n", g_checks);
   return 0;
 }
