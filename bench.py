@@ -165,6 +165,17 @@ def make_device_data(torch, device, n: int, seed: int):
 
 
 # ------------------------------------------------------------------- CPU baseline
+def cpu_model() -> str:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_baseline(host_np, budget_s: float, all_cores: bool = True) -> dict:
     """Single-thread AVX-512/AVX restatement of the reference's dispatched f32 path on a
     bounded sample; the all-cores variant is NOT something the reference does (labelled so)."""
@@ -185,7 +196,7 @@ def cpu_baseline(host_np, budget_s: float, all_cores: bool = True) -> dict:
         "sample": f"f32 x {host_np.size} elements ({nbytes >> 20} MiB, DRAM-resident), best of {len(times)} passes, "
                   "oracle/cpu_simd_f32.c (restatement of src/simd/simd_f32_ignore_nan.rs + generic.rs + task.rs), "
                   "1 thread as in the reference",
-        "host_cpus": os.cpu_count(), "result": list(res),
+        "host_cpus": os.cpu_count(), "cpu_model": cpu_model(), "result": list(res),
     }
     if all_cores:
         nt = os.cpu_count() or 1
@@ -235,7 +246,7 @@ def run_reference(args) -> int:
         "config": {"workload": "f32 1G elems ArgMinMax (ignore-NaN); reference arm runs a 2^27-element sample per step on the host CPU",
                    "elements_per_step": sample},
         "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": 1, "kind": "port",
-                         "isa": oracle.cpu_simd_isa(), "sample": sample_desc, "host_cpus": nt,
+                         "isa": oracle.cpu_simd_isa(), "sample": sample_desc, "host_cpus": nt, "cpu_model": cpu_model(),
                          "all_cores_not_reference": {"value": round(mt_gbs, 2), "threads": nt}},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
