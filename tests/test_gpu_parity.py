@@ -272,3 +272,39 @@ def test_cpp_device_slice_mirror():
     proc = subprocess.run([exe, "check"], capture_output=True, text=True, timeout=300)
     assert proc.returncode == 0, proc.stdout + proc.stderr
     assert proc.stdout.startswith("OK ")
+
+
+def test_host_slice_pageable_bounce_ring():
+    """Pageable host memory (numpy / Vec<T>) is bounced through a ring of pinned buffers filled by a
+    team of copy threads (host_slice.cu); pinned memory is read by the DMA engine directly.  Both
+    must give the oracle's answer, with extremes at chunk borders, in the last partial chunk and
+    in every bounce buffer of the ring, for several team sizes."""
+    import os
+
+    import torch
+
+    from argminmax_b200 import HostSlice, Workspace
+    rng = np.random.default_rng(61)
+    chunk = (32 << 20) // 4                       # elements per 32 MiB chunk
+    n = 7 * chunk + 12_345                        # 8 chunks: the 3-buffer ring wraps twice
+    a = rng.uniform(-1.0, 1.0, n).astype(np.float32)
+    for pos_lo, pos_hi in ((chunk - 1, chunk), (5 * chunk + 7, 3 * chunk - 1), (n - 1, n - 2), (0, 6 * chunk)):
+        b = a.copy()
+        b[[pos_lo, min(n - 1, pos_lo + 2 * chunk)]] = -2.0     # duplicates: the first must win
+        b[[pos_hi, min(n - 1, pos_hi + chunk + 1)]] = 2.0
+        exp = oracle.argminmax(b, 0)
+        pinned = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        pinned.numpy()[:] = b
+        for threads in ("1", "3", ""):
+            if threads:
+                os.environ["AMM_HOST_COPY_THREADS"] = threads
+            try:
+                ws = Workspace(0)
+                assert HostSlice.from_numpy(b, workspace=ws).argminmax() == exp, ("pageable", threads)
+                assert HostSlice.from_torch(pinned, workspace=ws).argminmax() == exp, ("pinned", threads)
+                b[n // 2] = np.nan
+                assert HostSlice.from_numpy(b, workspace=ws).nanargminmax() == (n // 2, n // 2)
+                b[n // 2] = 0.5
+                ws.close()
+            finally:
+                os.environ.pop("AMM_HOST_COPY_THREADS", None)
