@@ -685,19 +685,14 @@ static int host_window_bounds(const uint64_t* dev_offsets, uint64_t n, uint64_t 
   return AMM_OK;
 }
 
-// Few LARGE windows (1 MiB ... 64 MiB each, fewer than 4 per SM): one CTA per window would
-// leave most of the GPU idle and one streaming scan per window pays ~6 us each.  Instead every
-// window is cut into equal chunks (>= 128 KiB, about 16 per SM), the chunks run through the
-// ordinary windowed kernels as if they were windows -- thousands of them, so the whole GPU
-// streams -- and a combine kernel folds each window's chunk answers (first occurrence: the
-// lowest chunk wins ties).  One extra launch, < 1 % extra traffic.
-static int windows_chunked(int dtype, int slot, const void* dev_ptr, uint64_t n,
-                           const uint64_t* dev_offsets, uint64_t window, uint64_t n_windows,
-                           int mode, amm_workspace* ws, cudaStream_t stream, uint64_t* dev_out) {
-  const size_t es = amm_dtype_size(dtype);
-  std::vector<uint64_t> begins, ends;
-  int rc = host_window_bounds(dev_offsets, n, window, n_windows, stream, begins, ends);
-  if (rc) return rc;
+// Chunk plan of windows_chunked (pure host logic, unit-tested without a GPU through
+// amm_debug_plan_window_chunks): cuts the adjacent windows [begins[w], ends[w]) into equal pieces.
+// chunk k = [cuts[k], cuts[k+1]); window w owns chunks [first[w], first[w+1]).
+static int plan_window_chunks(const std::vector<uint64_t>& begins, const std::vector<uint64_t>& ends,
+                              size_t es, int sm_count, int chunks_per_sm, std::vector<uint64_t>& cuts,
+                              std::vector<uint64_t>& first) {
+  const uint64_t n_windows = begins.size();
+  if (n_windows == 0 || es == 0) return AMM_ERR_ARG;
   for (uint64_t w = 1; w < n_windows; ++w)
     if (begins[w] != ends[w - 1]) return kNotApplicable;  // not adjacent: caller falls back
   // Aim at ~16 equal chunks per SM (>= 128 KiB each, ~2400 in all): they run one per 256-thread
@@ -705,14 +700,16 @@ static int windows_chunked(int dtype, int slot, const void* dev_ptr, uint64_t n,
   // below 2 %.  Measured on 1 GiB with 4 / 8 / 16 / 32 / 64 chunks per SM: f32 269 x 4 MB windows
   // 4.9 / 5.6 / 5.9 / 5.9 / 5.4 TB/s, f64 135 x 8 MB -- / -- / 5.8 / 5.1 / 5.4 (at 32 the chunks
   // outnumber 4096 and go one per WARP, which for 8-byte dtypes is 1.4 resident rounds).
-  const uint64_t slots = (uint64_t)ws->sm_count * (uint64_t)ws->win_chunks_per_sm;
+  const uint64_t slots = (uint64_t)sm_count * (uint64_t)chunks_per_sm;
   const uint64_t span = ends[n_windows - 1] - begins[0];
-  uint64_t chunk = (span + (slots - n_windows) - 1) / (slots - n_windows);  // elements per chunk
+  const uint64_t room = slots > n_windows ? slots - n_windows : 1;
+  uint64_t chunk = (span + room - 1) / room;  // elements per chunk
   const uint64_t min_chunk = ((uint64_t)128 << 10) / es;
   if (chunk < min_chunk) chunk = min_chunk;
   // chunk k = [cuts[k], cuts[k+1]); window w owns chunks [first[w], first[w+1]) -- windows are
   // adjacent, so the last cut of one window is the first cut of the next
-  std::vector<uint64_t> cuts, first((size_t)n_windows + 1);
+  cuts.clear();
+  first.assign((size_t)n_windows + 1, 0);
   cuts.reserve((size_t)(span / chunk) + 2 * (size_t)n_windows + 2);
   cuts.push_back(begins[0]);
   for (uint64_t w = 0; w < n_windows; ++w) {
@@ -727,6 +724,25 @@ static int windows_chunked(int dtype, int slot, const void* dev_ptr, uint64_t n,
     cuts.push_back(ends[w]);
   }
   first[n_windows] = cuts.size() - 1;
+  return AMM_OK;
+}
+
+// Few LARGE windows (1 MiB ... 64 MiB each, fewer than 4 per SM): one CTA per window would
+// leave most of the GPU idle and one streaming scan per window pays ~6 us each.  Instead every
+// window is cut into equal chunks (>= 128 KiB, about 16 per SM), the chunks run through the
+// ordinary windowed kernels as if they were windows -- thousands of them, so the whole GPU
+// streams -- and a combine kernel folds each window's chunk answers (first occurrence: the
+// lowest chunk wins ties).  One extra launch, < 1 % extra traffic.
+static int windows_chunked(int dtype, int slot, const void* dev_ptr, uint64_t n,
+                           const uint64_t* dev_offsets, uint64_t window, uint64_t n_windows,
+                           int mode, amm_workspace* ws, cudaStream_t stream, uint64_t* dev_out) {
+  const size_t es = amm_dtype_size(dtype);
+  std::vector<uint64_t> begins, ends;
+  int rc = host_window_bounds(dev_offsets, n, window, n_windows, stream, begins, ends);
+  if (rc) return rc;
+  std::vector<uint64_t> cuts, first;
+  rc = plan_window_chunks(begins, ends, es, ws->sm_count, ws->win_chunks_per_sm, cuts, first);
+  if (rc) return rc;
   const uint64_t n_chunks = cuts.size() - 1;
   if (n_chunks == 0) return kNotApplicable;  // every window is empty: the plain kernels write the NO_INDEX pairs
   // scratch on the device: cuts | first | pairs
@@ -869,6 +885,26 @@ int amm_copy_to_host(int device, void* dst_host, const void* src_dev, size_t byt
   int rc = AMM_OK;
   (void)rc;
   AMM_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+  return AMM_OK;
+}
+
+/* Pure host logic of the chunked window path, exposed for the CPU test-suite: plans the chunks
+   of `n_windows` adjacent windows.  Returns AMM_OK, AMM_ERR_ARG, AMM_ERR_TOO_LARGE (outputs too
+   small) or 1000 when the windows are not adjacent (the path then does not apply). */
+int amm_debug_plan_window_chunks(const uint64_t* begins, const uint64_t* ends, uint64_t n_windows,
+                                 size_t elem_size, int sm_count, int chunks_per_sm,
+                                 uint64_t* cuts_out, uint64_t cuts_capacity, uint64_t* n_cuts,
+                                 uint64_t* first_out) {
+  if (!begins || !ends || !cuts_out || !n_cuts || !first_out || sm_count < 1 || chunks_per_sm < 1)
+    return AMM_ERR_ARG;
+  std::vector<uint64_t> b(begins, begins + n_windows), e(ends, ends + n_windows), cuts, first;
+  const int rc = plan_window_chunks(b, e, elem_size, sm_count, chunks_per_sm, cuts, first);
+  if (rc == kNotApplicable) return 1000;
+  if (rc) return rc;
+  if (cuts.size() > cuts_capacity) return AMM_ERR_TOO_LARGE;
+  memcpy(cuts_out, cuts.data(), cuts.size() * sizeof(uint64_t));
+  memcpy(first_out, first.data(), first.size() * sizeof(uint64_t));
+  *n_cuts = cuts.size();
   return AMM_OK;
 }
 

@@ -288,6 +288,14 @@ const char* amm_variant_name(int variant);
    (no binding overhead): out_us = {median, min, p99} microseconds over `calls` calls. */
 int amm_measure_call_latency(int dtype, const void* dev_ptr, uint64_t n, int mode,
                              amm_workspace* ws, void* stream, int calls, double out_us[3]);
+/* Test hook (pure host logic, needs no GPU): the chunk plan the windowed form uses for few
+   large adjacent windows.  chunk k = [cuts[k], cuts[k+1]); window w owns chunks
+   [first[w], first[w+1]).  `first_out` holds n_windows + 1 entries.  Returns 1000 when the
+   windows are not adjacent. */
+int amm_debug_plan_window_chunks(const uint64_t* begins, const uint64_t* ends, uint64_t n_windows,
+                                 size_t elem_size, int sm_count, int chunks_per_sm,
+                                 uint64_t* cuts_out, uint64_t cuts_capacity, uint64_t* n_cuts,
+                                 uint64_t* first_out);
 /* grid size and kernels launched by the most recent amm_argminmax_launch on ws */
 int amm_workspace_last_launch(const amm_workspace* ws, int* grid, int* threads, uint64_t* launches_total);
 
