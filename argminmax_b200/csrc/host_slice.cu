@@ -31,6 +31,7 @@ struct amm_host_pipeline {
   void* bounce[kBounce];         // pinned, chunk_bytes each, allocated on first pageable call
   cudaEvent_t bounce_done[kBounce];  // H2D out of bounce[i] has completed
   int copy_threads;
+  size_t bounce_bytes;  // chunk size of the bounced (pageable) path, <= chunk_bytes
 };
 
 namespace {
@@ -102,6 +103,10 @@ static int pipeline_create(amm_workspace* ws) {
   }
   int hw = (int)std::thread::hardware_concurrency();
   p->copy_threads = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1);
+  p->bounce_bytes = (size_t)16 << 20;
+  const char* bb = getenv("AMM_HOST_BOUNCE_MB");
+  if (bb && atoi(bb) > 0) p->bounce_bytes = (size_t)atoi(bb) << 20;
+  if (p->bounce_bytes > p->chunk_bytes) p->bounce_bytes = p->chunk_bytes;
   const char* ct = getenv("AMM_HOST_COPY_THREADS");
   if (ct && atoi(ct) > 0 && atoi(ct) <= 64) p->copy_threads = atoi(ct);
   ws->pipe = p;
@@ -156,7 +161,18 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
   }
   amm_host_pipeline* p = ws->pipe;
   const size_t es = amm_dtype_size(dtype);
-  const uint64_t chunk_elems = p->chunk_bytes / es;
+  // pageable input of more than one chunk: bounce through pinned memory (see the file header),
+  // in smaller chunks -- with 16 MiB the three bounce buffers stay in the host's last-level
+  // cache, so the DMA engine reads what the copy threads just wrote without a DRAM round trip
+  // (measured, 1 GiB f32: 53 GB/s at 16 MiB chunks, 32-44 at 32 MiB, 29-40 at 128 MiB)
+  bool bounce = false;
+  if (n * es > p->chunk_bytes && p->copy_threads > 0 && !getenv("AMM_HOST_NO_BOUNCE")) {
+    cudaPointerAttributes attr;
+    const cudaError_t e = cudaPointerGetAttributes(&attr, host_ptr);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    bounce = (e != cudaSuccess) || attr.type == cudaMemoryTypeUnregistered;
+  }
+  const uint64_t chunk_elems = (bounce ? p->bounce_bytes : p->chunk_bytes) / es;
   const uint64_t nchunks = (n + chunk_elems - 1) / chunk_elems;
   for (int i = 0; i < 2; ++i) {
     amm_workspace_set_tuning(p->child[i], ws->threads, ws->ctas_per_sm, ws->variant);
@@ -171,17 +187,9 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
   recs.clear();
   recs.reserve((size_t)nchunks);
   const uint8_t* src = (const uint8_t*)host_ptr;
-  // pageable input of more than one chunk: bounce through pinned memory (see the file header)
-  bool bounce = false;
-  if (nchunks > 1 && p->copy_threads > 0 && !getenv("AMM_HOST_NO_BOUNCE")) {
-    cudaPointerAttributes attr;
-    const cudaError_t e = cudaPointerGetAttributes(&attr, host_ptr);
-    if (e != cudaSuccess) (void)cudaGetLastError();
-    bounce = (e != cudaSuccess) || attr.type == cudaMemoryTypeUnregistered;
-  }
   if (bounce && !p->bounce[0]) {
     for (int i = 0; i < kBounce; ++i) {
-      AMM_CUDA(cudaHostAlloc(&p->bounce[i], p->chunk_bytes, cudaHostAllocDefault));
+      AMM_CUDA(cudaHostAlloc(&p->bounce[i], p->bounce_bytes, cudaHostAllocDefault));
       AMM_CUDA(cudaEventCreateWithFlags(&p->bounce_done[i], cudaEventDisableTiming));
     }
   }
