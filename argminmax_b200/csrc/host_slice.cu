@@ -151,7 +151,6 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
   int rc = AMM_OK;
-  (void)rc;
   if (!ws->pipe) {
     rc = pipeline_create(ws);
     if (rc) {

@@ -87,22 +87,8 @@ static int policy_slot(int dtype, int mode) {
 }
 
 static int dispatch(amm_workspace* ws, int dtype, int mode, ScanParams& p, cudaStream_t stream) {
-  const bool ret = (mode == AMM_RETURN_NAN);
-  int slot;
-  switch (dtype) {
-    case AMM_I8: slot = 0; break;
-    case AMM_I16: slot = 1; break;
-    case AMM_I32: slot = 2; break;
-    case AMM_I64: slot = 3; break;
-    case AMM_U8: slot = 4; break;
-    case AMM_U16: slot = 5; break;
-    case AMM_U32: slot = 6; break;
-    case AMM_U64: slot = 7; break;
-    case AMM_F16: slot = ret ? 9 : 8; break;
-    case AMM_F32: slot = ret ? 11 : 10; break;
-    case AMM_F64: slot = ret ? 13 : 12; break;
-    default: return AMM_ERR_ARG;
-  }
+  const int slot = policy_slot(dtype, mode);
+  if (slot < 0) return AMM_ERR_ARG;
   return launch_slot(slot, ws, p, stream);
 }
 
@@ -144,8 +130,6 @@ int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global
   if (((uintptr_t)dev_ptr) % es != 0) return AMM_ERR_ALIGN;
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
-  int rc = AMM_OK;
-  (void)rc;
   ScanParams p;
   memset(&p, 0, sizeof(p));
   p.base = (const uint8_t*)dev_ptr;
@@ -284,8 +268,6 @@ int amm_combine_records_launch(const void* dev_records, int count, int mode, amm
   if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
-  int rc = AMM_OK;
-  (void)rc;
   combine_records_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(
       (const amm_record*)dev_records, count, mode, ws->rec_dev, ws->rec_host_dev, ++ws->seq);
   AMM_CUDA(cudaGetLastError());
@@ -359,7 +341,6 @@ int amm_workspace_create(int device, amm_workspace** out) {
   DeviceGuard guard(device);
   if (guard.rc) return guard.rc;
   int rc = AMM_OK;
-  (void)rc;
   amm_workspace* ws = new (std::nothrow) amm_workspace();
   if (!ws) return AMM_ERR_ARG;
   rc = workspace_init(ws, device);
@@ -398,8 +379,6 @@ int amm_exchange_create(amm_workspace* ws, int world, int rank, void* ipc_handle
   if (!ws || world < 2 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return AMM_ERR_ARG;
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
-  int rc = AMM_OK;
-  (void)rc;
   exchange_destroy(ws);
   const size_t bytes = (size_t)2 * world * XCHG_SLOT_WORDS * sizeof(uint64_t);
   AMM_CUDA(cudaMalloc((void**)&ws->xbuf, bytes));
@@ -434,8 +413,6 @@ int amm_exchange_connect_ipc(amm_workspace* ws, const void* ipc_handles) {
   if (!ws || !ipc_handles || ws->xworld < 2) return AMM_ERR_ARG;
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
-  int rc = AMM_OK;
-  (void)rc;
   uint64_t* table[XCHG_MAX_WORLD];
   for (int r = 0; r < ws->xworld; ++r) {
     if (r == ws->xrank) {
@@ -456,8 +433,6 @@ int amm_exchange_connect_ptrs(amm_workspace* ws, void* const* peer_buffers) {
   if (!ws || !peer_buffers || ws->xworld < 2) return AMM_ERR_ARG;
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
-  int rc = AMM_OK;
-  (void)rc;
   uint64_t* table[XCHG_MAX_WORLD];
   for (int r = 0; r < ws->xworld; ++r) table[r] = (uint64_t*)peer_buffers[r];
   table[ws->xrank] = ws->xbuf;
@@ -796,7 +771,6 @@ static int windows_common(int dtype, const void* dev_ptr, uint64_t n, const uint
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
   int rc = AMM_OK;
-  (void)rc;
   WindowParams p;
   p.base = (const uint8_t*)dev_ptr;
   p.n = n;
@@ -855,8 +829,6 @@ int amm_device_alloc(int device, size_t bytes, void** dev_ptr) {
   if (!dev_ptr) return AMM_ERR_ARG;
   DeviceGuard guard(device);
   if (guard.rc) return guard.rc;
-  int rc = AMM_OK;
-  (void)rc;
   AMM_CUDA(cudaMalloc(dev_ptr, bytes ? bytes : 1));
   return AMM_OK;
 }
@@ -864,8 +836,6 @@ int amm_device_alloc(int device, size_t bytes, void** dev_ptr) {
 int amm_device_free(int device, void* dev_ptr) {
   DeviceGuard guard(device);
   if (guard.rc) return guard.rc;
-  int rc = AMM_OK;
-  (void)rc;
   AMM_CUDA(cudaFree(dev_ptr));
   return AMM_OK;
 }
@@ -873,8 +843,6 @@ int amm_device_free(int device, void* dev_ptr) {
 int amm_copy_to_device(int device, void* dst_dev, const void* src_host, size_t bytes) {
   DeviceGuard guard(device);
   if (guard.rc) return guard.rc;
-  int rc = AMM_OK;
-  (void)rc;
   AMM_CUDA(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
   return AMM_OK;
 }
@@ -882,8 +850,6 @@ int amm_copy_to_device(int device, void* dst_dev, const void* src_host, size_t b
 int amm_copy_to_host(int device, void* dst_host, const void* src_dev, size_t bytes) {
   DeviceGuard guard(device);
   if (guard.rc) return guard.rc;
-  int rc = AMM_OK;
-  (void)rc;
   AMM_CUDA(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
   return AMM_OK;
 }
