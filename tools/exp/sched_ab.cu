@@ -5,6 +5,10 @@
 //   0  static grid-stride over tiles (what argminmax_scan_kernel does)
 //   1  dynamic: CTAs claim batches of B tiles from a global counter (claim issued a batch ahead)
 //   2  static contiguous: CTA c streams tiles [c*per, (c+1)*per)
+//   3  dynamic per WARP, no CTA barrier: a warp-tile is 32 lanes x U vectors (2 KiB); every warp
+//      claims batches of B warp-tiles with its lane 0 (claim issued one batch ahead, broadcast by
+//      shuffle) -- the barrier-free variant left open by profiles/r01d_schedule_experiment.md
+//   4  static per warp: warp w streams warp-tiles w, w + W, ... (control for the access pattern of 3)
 // Prints kernel time (CUDA events) and the spread of per-CTA finish times (globaltimer).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/exp/bin/sched_ab tools/exp/sched_ab.cu
 #include <cuda_runtime.h>
@@ -53,7 +57,10 @@ struct Args {
   const uint8_t* base;
   uint32_t n_tiles;
   uint32_t batch;      // tiles per claim (mode 1)
-  uint32_t* counter;   // mode 1, zeroed before the launch
+  uint32_t* counter;   // modes 1 and 3, zeroed before the launch
+  uint32_t wrap;       // 0xFFFFFFFF: bound of atom.inc (== add 1); a runtime value so that ptxas
+                       // cannot turn it into an add and warp-aggregate it (ATOMG + SHFL of the
+                       // result at issue time would stall the warp's next loads)
   unsigned long long* t0;
   unsigned long long* t1;
   float* sink;
@@ -146,6 +153,77 @@ __global__ void __launch_bounds__(256) stream_kernel(const Args a) {
   if (mn == 123.456f && mx == 654.321f) a.sink[0] = mn;  // keep the folds alive
 }
 
+__device__ __forceinline__ uint32_t claim_raw(const Args& a) {
+  uint32_t r;
+  asm volatile("atom.global.inc.u32 %0, [%1], %2;" : "=r"(r) : "l"(a.counter), "r"(a.wrap));
+  return r;
+}
+
+// modes 3 / 4: the unit of scheduling is a WARP (tile = 32 lanes x U x 32 B = 2 KiB)
+template <int MODE>
+__global__ void __launch_bounds__(256) stream_warp_kernel(const Args a) {
+  const unsigned long long tb = gtime();
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
+  constexpr uint64_t WT_BYTES = 32ull * U * VEC;  // bytes per warp-tile
+  const uint32_t nwt = a.n_tiles * (blockDim.x >> 5);  // warp-tiles in the array (CTA tile = 8 of them)
+  const uint8_t* lane_base = a.base + (uint64_t)lane * VEC;
+  const uint64_t jstride = 32ull * VEC;
+  float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+  const uint32_t B = a.batch;
+  const uint32_t nb = (nwt + B - 1) / B;
+  uint32_t b_cur = warp_global, b_next = warp_global + n_warps, i_in = 0, pending = 0;
+  if (MODE == 3 && lane == 0 && b_next < nb) pending = claim_raw(a);  // consumed one batch later
+  uint32_t t = b_cur < nb ? b_cur * B : NONE;
+  auto next_tile = [&](uint32_t cur) -> uint32_t {
+    ++i_in;
+    const uint32_t n = cur + 1;
+    if (i_in < B && n < nwt) return n;
+    if (b_next >= nb) return NONE;
+    b_cur = b_next;
+    i_in = 0;
+    if (MODE == 3) {
+      const uint32_t claimed = 2u * n_warps + __shfl_sync(0xFFFFFFFFu, pending, 0);
+      b_next = claimed;
+      if (lane == 0 && b_next < nb) pending = claim_raw(a);
+    } else {
+      b_next = b_cur + n_warps;
+    }
+    return b_cur * B;
+  };
+  uint32_t va[U][NW], vb[U][NW];
+  if (t != NONE) {
+    const uint8_t* q = lane_base + (uint64_t)t * WT_BYTES;
+#pragma unroll
+    for (int j = 0; j < U; ++j) ld8(q + j * jstride, va[j]);
+  }
+  while (t != NONE) {
+    const uint32_t t1 = next_tile(t);
+    if (t1 != NONE) {
+      const uint8_t* q = lane_base + (uint64_t)t1 * WT_BYTES;
+#pragma unroll
+      for (int j = 0; j < U; ++j) ld8(q + j * jstride, vb[j]);
+    }
+    fold(va, mn, mx);
+    if (t1 == NONE) break;
+    const uint32_t t2 = next_tile(t1);
+    if (t2 != NONE) {
+      const uint8_t* q = lane_base + (uint64_t)t2 * WT_BYTES;
+#pragma unroll
+      for (int j = 0; j < U; ++j) ld8(q + j * jstride, va[j]);
+    }
+    fold(vb, mn, mx);
+    t = t2;
+  }
+  const unsigned long long te = gtime();
+  if (threadIdx.x == 0) {
+    a.t0[blockIdx.x] = tb;
+    a.t1[blockIdx.x] = te;
+  }
+  if (mn == 123.456f && mx == 654.321f) a.sink[0] = mn;
+}
+
 template <int MODE>
 static void run(const char* name, const Args& a0, int grid, int reps, uint64_t bytes) {
   Args a = a0;
@@ -156,7 +234,11 @@ static void run(const char* name, const Args& a0, int grid, int reps, uint64_t b
   for (int r = 0; r < reps + 3; ++r) {
     CK(cudaMemsetAsync(a.counter, 0, 4));
     CK(cudaEventRecord(e0));
-    stream_kernel<MODE><<<grid, 256>>>(a);
+    if (MODE >= 3) {
+      stream_warp_kernel<MODE><<<grid, 256>>>(a);
+    } else {
+      stream_kernel<(MODE >= 3 ? 0 : MODE)><<<grid, 256>>>(a);
+    }
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float m;
@@ -194,6 +276,7 @@ int main(int argc, char** argv) {
   CK(cudaMemset(buf, 0x3c, bytes));
   Args a;
   a.base = buf;
+  a.wrap = 0xFFFFFFFFu;
   a.n_tiles = (uint32_t)(bytes / (256ull * U * VEC));
   CK(cudaMalloc(&a.counter, 4));
   CK(cudaMalloc(&a.t0, 8 * 4096));
@@ -209,6 +292,11 @@ int main(int argc, char** argv) {
     for (uint32_t b : {1u, 2u, 4u, 8u, 32u}) {
       a.batch = b;
       run<1>("dynamic", a, grid, reps, bytes);
+    }
+    for (uint32_t b : {8u, 32u, 128u}) {  // warp-tiles (2 KiB) per claim: 16 / 64 / 256 KiB
+      a.batch = b;
+      run<4>("static_per_warp", a, grid, reps, bytes);
+      run<3>("dynamic_per_warp", a, grid, reps, bytes);
     }
   }
   return 0;
