@@ -119,6 +119,17 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------ NUMA
+def parse_cpulist(spec: str) -> set:
+    """sysfs cpulist ("0-3,8-11,16") -> set of CPU ids."""
+    cpus = set()
+    for part in spec.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa_node(torch, index: int) -> dict:
     """Run this rank (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA
     node its GPU hangs off -- what `numactl --cpunodebind` does for one-rank-per-GPU jobs.  With 8
@@ -136,11 +147,7 @@ def bind_to_gpu_numa_node(torch, index: int) -> dict:
             return info
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             spec = f.read().strip()
-        cpus = set()
-        for part in spec.split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
+        cpus = parse_cpulist(spec) & os.sched_getaffinity(0)
         if cpus:
             os.sched_setaffinity(0, cpus)
             info["cpus"] = len(cpus)
