@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libargminmax_b200.so")
 STAMP = os.path.join(LIB_DIR, "build.stamp")
 SOURCES = ["libamm.cu", "host_slice.cu", "sharded.cu", "scan_inst.cu"]
-HEADERS = ["amm_internal.h", "policies.cuh", "scan_kernel.cuh", "scan_launch.cuh", "windows_kernel.cuh",
+HEADERS = ["amm_internal.h", "record_slot.h", "policies.cuh", "scan_kernel.cuh", "scan_launch.cuh", "windows_kernel.cuh",
            os.path.join("..", "..", "include", "argminmax_b200.h")]
 N_GROUPS = 7  # scan_inst.cu is compiled once per policy group (-DAMM_GROUP=k), in parallel
 NVCC_FLAGS = [
@@ -103,6 +103,21 @@ def build_boundscheck(force: bool = False) -> str:
                 return DEBUG_LIB_PATH
     return _build_into(DEBUG_LIB_PATH, DEBUG_STAMP, OBJ_DIR + "_boundscheck",
                        ["-DAMM_BOUNDS_CHECK"], False)
+
+
+STAMPS_LIB_PATH = os.path.join(LIB_DIR, "libargminmax_b200_stamps.so")
+STAMPS_STAMP = os.path.join(LIB_DIR, "build_stamps.stamp")
+
+
+def build_stamps(force: bool = False) -> str:
+    """Debug twin (-DAMM_PHASE_STAMPS): thread 0 of every CTA records %globaltimer at the phase
+    boundaries of a scan (amm_debug_read_stamps).  Used by tools/phase_stamps.py to attribute
+    the fixed per-call cost; never loaded by the product path."""
+    if not force and os.path.exists(STAMPS_LIB_PATH) and os.path.exists(STAMPS_STAMP):
+        with open(STAMPS_STAMP) as f:
+            if f.read().strip() == _fingerprint():
+                return STAMPS_LIB_PATH
+    return _build_into(STAMPS_LIB_PATH, STAMPS_STAMP, OBJ_DIR + "_stamps", ["-DAMM_PHASE_STAMPS"], False)
 
 
 if __name__ == "__main__":

@@ -64,7 +64,12 @@ SIGNATURES = {
     "amm_workspace_host_record": (_i, [_vp, ctypes.POINTER(ctypes.POINTER(AmmRecord))]),
     "amm_combine_records": (_i, [ctypes.POINTER(AmmRecord), _i, _i, _u64p]),
     "amm_exchange_create": (_i, [_vp, _i, _i, _vp]),
-    "amm_exchange_connect_ipc": (_i, [_vp, _vp]),
+    "amm_exchange_connect_ipc": (_i, [_vp, _vp, _vp]),
+    "amm_exchange_set_timeout": (_i, [_vp, _u64]),
+    "amm_exchange_disconnect": (_i, [_vp]),
+    "amm_exchange_destroy": (_i, [_vp]),
+    "amm_device_uuid": (_i, [_i, _vp]),
+    "amm_debug_read_stamps": (_i, [_vp, _u64p, _i]),
     "amm_exchange_connect_ptrs": (_i, [_vp, ctypes.POINTER(_vp)]),
     "amm_exchange_local_buffer": (_i, [_vp, ctypes.POINTER(_vp)]),
     "amm_argminmax_launch_exchange": (_i, [_i, _vp, _u64, _i, _u64, _vp, _vp]),

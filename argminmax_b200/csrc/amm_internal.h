@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "../../include/argminmax_b200.h"
+#include "record_slot.h"
 
 namespace amm {
 extern thread_local int g_last_cuda_error;
@@ -23,7 +24,7 @@ struct amm_host_pipeline;  // host_slice.cu
 
 // 14 policy slots (8 ints + 3 floats x 2 modes) x load-shape variants
 constexpr int AMM_POLICY_SLOTS = 14;
-constexpr int AMM_MAX_VARIANTS = 16;
+constexpr int AMM_MAX_VARIANTS = 32;
 
 struct amm_workspace {
   int device;
@@ -39,6 +40,10 @@ struct amm_workspace {
   int direct_threads, direct_ctas_per_sm;
   int direct_vecs_per_thread;  // target vectors per thread when sizing the latency kernel's grid
   int direct_packed;      // 32-bit keys: packed-word atomics instead of partials (AMM_DIRECT_PACKED=0: off)
+  int scan_packed;        // the same cross-CTA step in the streaming kernel (AMM_SCAN_PACKED=0: off)
+  int scan_dyn_pct;       // share of the tiles claimed at run time: -1 automatic, 0 none, 1..90 percent (AMM_SCAN_DYN_PCT)
+  int scan_contig;        // tile partition of the streaming kernel: -1 automatic, 0 grid-stride, 1 contiguous ranges
+  uint64_t direct_elems32, direct_elems64;  // direct_auto: latency kernel up to this many elements (32- / 64-bit keys)
   int occupancy[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];      // cached CTAs/SM ...
   int occupancy_threads[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // ... for this CTA size
   size_t static_smem[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];   // static smem of the kernel + 1 (0 = not queried)
@@ -70,6 +75,9 @@ struct amm_workspace {
   uint64_t** xpeers_dev;     // device array [world] of peer-mapped buffer pointers
   void* xopened[16];         // pointers obtained from cudaIpcOpenMemHandle (to close)
   uint64_t xseq;
+  uint64_t xtimeout_ms;      // in-kernel wait for a peer's record (0 = for ever); amm_exchange_set_timeout
+  int xbroken;               // a call timed out: the banks are out of step, the exchange must be re-created
+  uint64_t* stamps;          // AMM_PHASE_STAMPS builds: max_grid x 8 device words (else nullptr)
 };
 
 namespace amm {
@@ -98,6 +106,8 @@ struct DeviceGuard {
   DeviceGuard& operator=(const DeviceGuard&) = delete;
 };
 int set_device(int device);
+// argument checks of one scan (what `launch` would reject), without touching the device
+int validate_scan(int dtype, const void* dev_ptr, uint64_t n, int mode, bool empty_allowed);
 int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global_offset,
            amm_workspace* ws, cudaStream_t stream, void* dev_record_out, bool exchange = false);
 void exchange_destroy(amm_workspace* ws);

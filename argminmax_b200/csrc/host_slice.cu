@@ -179,6 +179,11 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
     p->child[i]->direct_auto = ws->direct_auto;
     p->child[i]->direct_packed = ws->direct_packed;
     p->child[i]->direct_vecs_per_thread = ws->direct_vecs_per_thread;
+    p->child[i]->direct_elems32 = ws->direct_elems32;
+    p->child[i]->direct_elems64 = ws->direct_elems64;
+    p->child[i]->scan_packed = ws->scan_packed;
+    p->child[i]->scan_contig = ws->scan_contig;
+    p->child[i]->scan_dyn_pct = ws->scan_dyn_pct;
     p->child[i]->pdl = ws->pdl;
     p->child[i]->direct_threads = ws->direct_threads;
     p->child[i]->direct_ctas_per_sm = ws->direct_ctas_per_sm;

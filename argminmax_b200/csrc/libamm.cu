@@ -99,9 +99,7 @@ bool read_host_slot(const amm_workspace* ws, uint64_t want, amm_record* out) {
   if (h[7] != want) return false;
   uint64_t w[9];
   for (int i = 0; i < 9; ++i) w[i] = h[i];
-  uint64_t c = 0xA5A5C3C3F00DBEEFull;
-  for (int i = 0; i < 8; ++i) c ^= w[i];
-  if (c != w[8] || w[7] != want) return false;
+  if (mix_checksum(w, HOST_SLOT_SEED) != w[8] || w[7] != want) return false;
   memcpy(out, w, sizeof(amm_record));
   return true;
 }
@@ -113,21 +111,32 @@ int set_device(int device) {
   return AMM_OK;
 }
 
-int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global_offset,
-           amm_workspace* ws, cudaStream_t stream, void* dev_record_out, bool exchange) {
-  if (ws == nullptr) return AMM_ERR_ARG;
+int validate_scan(int dtype, const void* dev_ptr, uint64_t n, int mode, bool empty_allowed) {
   if (dtype < 0 || dtype >= AMM_DTYPE_COUNT) return AMM_ERR_ARG;
   if (mode != AMM_IGNORE_NAN && mode != AMM_RETURN_NAN) return AMM_ERR_ARG;
-  if (exchange) {
-    // an empty shard still takes part in the exchange (it contributes "no value")
-    if (ws->xworld < 2 || !ws->xpeers_dev) return AMM_ERR_ARG;
+  if (empty_allowed) {
     if (n != 0 && dev_ptr == nullptr) return AMM_ERR_ARG;
   } else {
     if (dev_ptr == nullptr) return AMM_ERR_ARG;
     if (n == 0) return AMM_ERR_EMPTY;
   }
+  if (((uintptr_t)dev_ptr) % amm_dtype_size(dtype) != 0) return AMM_ERR_ALIGN;
+  return AMM_OK;
+}
+
+int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global_offset,
+           amm_workspace* ws, cudaStream_t stream, void* dev_record_out, bool exchange) {
+  if (ws == nullptr) return AMM_ERR_ARG;
+  if (exchange) {
+    // an empty shard still takes part in the exchange (it contributes "no value")
+    if (ws->xworld < 2 || !ws->xpeers_dev) return AMM_ERR_ARG;
+    if (ws->xbroken) return AMM_ERR_PEER;  // an earlier call timed out: re-create the exchange
+  }
+  {
+    const int vrc = validate_scan(dtype, dev_ptr, n, mode, exchange);
+    if (vrc) return vrc;
+  }
   const size_t es = amm_dtype_size(dtype);
-  if (((uintptr_t)dev_ptr) % es != 0) return AMM_ERR_ALIGN;
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
   ScanParams p;
@@ -147,7 +156,7 @@ int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global
   p.ticket = ws->ticket;
   p.rec_dev = dev_record_out ? (amm_record*)dev_record_out : ws->rec_dev;
   p.rec_host = ws->rec_host_dev;
-  p.seq = ++ws->seq;
+  p.seq = ws->seq + 1;  // committed below, once the kernel is really on the stream
   p.mode = mode;
   p.publish_fence = ws->publish_fence;
   p.pipelined = (ws->pdl && ws->pipelined) ? 1 : 0;
@@ -155,9 +164,18 @@ int launch(int dtype, const void* dev_ptr, uint64_t n, int mode, uint64_t global
     p.world = ws->xworld;
     p.rank = ws->xrank;
     p.peer_slots = ws->xpeers_dev;
-    p.xseq = ++ws->xseq;
+    p.xseq = ws->xseq + 1;
+    p.xtimeout_ns = ws->xtimeout_ms * 1000000ull;
   }
-  return dispatch(ws, dtype, mode, p, stream);
+  p.stamps = ws->stamps;
+  const int rc = dispatch(ws, dtype, mode, p, stream);
+  // the exchange sequence number only advances when the kernel really went out: a rank whose
+  // launch failed must not get out of step with its peers' tags
+  if (rc == AMM_OK) {
+    ws->seq += 1;
+    if (exchange) ws->xseq += 1;
+  }
+  return rc;
 }
 
 void exchange_destroy(amm_workspace* ws) {
@@ -170,6 +188,7 @@ void exchange_destroy(amm_workspace* ws) {
   ws->xpeers_dev = nullptr;
   ws->xbuf = nullptr;
   ws->xworld = 0;
+  ws->xbroken = 0;
 }
 
 // Fold records (ascending shard order) into one record.  Strict compares on the key,
@@ -299,6 +318,12 @@ static int workspace_init(amm_workspace* ws, int device) {
   if (getenv("AMM_DIRECT_THREADS")) ws->direct_threads = atoi(getenv("AMM_DIRECT_THREADS"));
   if (getenv("AMM_DIRECT_CTAS")) ws->direct_ctas_per_sm = atoi(getenv("AMM_DIRECT_CTAS"));
   ws->direct_packed = getenv("AMM_DIRECT_PACKED") ? atoi(getenv("AMM_DIRECT_PACKED")) : 1;
+  ws->scan_packed = getenv("AMM_SCAN_PACKED") ? atoi(getenv("AMM_SCAN_PACKED")) : 1;
+  ws->scan_contig = getenv("AMM_SCAN_CONTIG") ? atoi(getenv("AMM_SCAN_CONTIG")) : -1;
+  ws->scan_dyn_pct = getenv("AMM_SCAN_DYN_PCT") ? atoi(getenv("AMM_SCAN_DYN_PCT")) : -1;
+  ws->direct_elems32 = getenv("AMM_DIRECT_ELEMS32") ? strtoull(getenv("AMM_DIRECT_ELEMS32"), nullptr, 10) : (1ull << 20);
+  ws->direct_elems64 = getenv("AMM_DIRECT_ELEMS64") ? strtoull(getenv("AMM_DIRECT_ELEMS64"), nullptr, 10) : (1ull << 16);
+  ws->xtimeout_ms = getenv("AMM_PEER_TIMEOUT_MS") ? strtoull(getenv("AMM_PEER_TIMEOUT_MS"), nullptr, 10) : 60000;
   ws->direct_vecs_per_thread = getenv("AMM_DIRECT_VPT") ? atoi(getenv("AMM_DIRECT_VPT")) : 1;
   if (ws->direct_vecs_per_thread < 1 || ws->direct_vecs_per_thread > 16) ws->direct_vecs_per_thread = 1;
   if (ws->direct_threads < 64 || ws->direct_threads > MAX_THREADS || ws->direct_threads % 32)
@@ -319,7 +344,9 @@ static int workspace_init(amm_workspace* ws, int device) {
   AMM_CUDA(cudaMalloc(&ws->partials, (size_t)ws->max_grid * 64));
   AMM_CUDA(cudaMalloc((void**)&ws->ticket, 256));
   AMM_CUDA(cudaMemset(ws->ticket, 0, 256));
-  {  // packed candidate words of the latency kernel start at their identities (packed_finish)
+  // words of the ticket block: [0] ticket, [8] bounds-check error count, [16..21] packed candidate
+  // words, [24] claim counter of the dynamic tail
+  {  // packed candidate words start at their identities (packed_grid_reduce)
     const unsigned long long ident[3] = {PACK_MIN_NONE, PACK_MAX_NONE, POS_NONE};
     AMM_CUDA(cudaMemcpy(ws->ticket + 16, ident, sizeof(ident), cudaMemcpyHostToDevice));
   }
@@ -328,6 +355,10 @@ static int workspace_init(amm_workspace* ws, int device) {
   AMM_CUDA(cudaHostAlloc((void**)&ws->rec_host, 128, cudaHostAllocMapped));
   memset(ws->rec_host, 0, 128);
   AMM_CUDA(cudaHostGetDevicePointer((void**)&ws->rec_host_dev, ws->rec_host, 0));
+#ifdef AMM_PHASE_STAMPS
+  AMM_CUDA(cudaMalloc((void**)&ws->stamps, (size_t)ws->max_grid * 8 * sizeof(uint64_t)));
+  AMM_CUDA(cudaMemset(ws->stamps, 0, (size_t)ws->max_grid * 8 * sizeof(uint64_t)));
+#endif
   AMM_CUDA(cudaDeviceSynchronize());
   return AMM_OK;
 }
@@ -360,6 +391,7 @@ int amm_workspace_destroy(amm_workspace* ws) {
   host_pipeline_destroy(ws);
   exchange_destroy(ws);
   if (ws->win_scratch) cudaFree(ws->win_scratch);
+  if (ws->stamps) cudaFree(ws->stamps);
   if (ws->partials) cudaFree(ws->partials);
   if (ws->ticket) cudaFree(ws->ticket);
   if (ws->rec_dev) cudaFree(ws->rec_dev);
@@ -377,9 +409,11 @@ int amm_argminmax_launch(int dtype, const void* dev_ptr, uint64_t n, int mode,
 /* ---- fused cross-GPU exchange: setup ------------------------------------------------- */
 int amm_exchange_create(amm_workspace* ws, int world, int rank, void* ipc_handle_out) {
   if (!ws || world < 2 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world) return AMM_ERR_ARG;
+  // One exchange per workspace: silently replacing a live one would free a buffer that peers
+  // still have mapped (cudaIpcOpenMemHandle) and reset the sequence numbers under its user.
+  if (ws->xbuf != nullptr) return AMM_ERR_ARG;
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
-  exchange_destroy(ws);
   const size_t bytes = (size_t)2 * world * XCHG_SLOT_WORDS * sizeof(uint64_t);
   AMM_CUDA(cudaMalloc((void**)&ws->xbuf, bytes));
   AMM_CUDA(cudaMemset(ws->xbuf, 0, bytes));
@@ -397,6 +431,34 @@ int amm_exchange_create(amm_workspace* ws, int world, int rank, void* ipc_handle
   return AMM_OK;
 }
 
+int amm_exchange_set_timeout(amm_workspace* ws, uint64_t milliseconds) {
+  if (!ws) return AMM_ERR_ARG;
+  ws->xtimeout_ms = milliseconds;
+  return AMM_OK;
+}
+
+int amm_exchange_disconnect(amm_workspace* ws) {
+  if (!ws) return AMM_ERR_ARG;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  for (int i = 0; i < 16; ++i) {
+    if (ws->xopened[i]) cudaIpcCloseMemHandle(ws->xopened[i]);
+    ws->xopened[i] = nullptr;
+  }
+  (void)cudaGetLastError();
+  ws->xbroken = 1;  // no peer table any more: launches are refused until re-created
+  return AMM_OK;
+}
+
+int amm_exchange_destroy(amm_workspace* ws) {
+  if (!ws) return AMM_ERR_ARG;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  exchange_destroy(ws);
+  (void)cudaGetLastError();
+  return AMM_OK;
+}
+
 int amm_exchange_local_buffer(amm_workspace* ws, void** dev_ptr) {
   if (!ws || !dev_ptr || !ws->xbuf) return AMM_ERR_ARG;
   *dev_ptr = ws->xbuf;
@@ -409,8 +471,25 @@ static int exchange_upload(amm_workspace* ws, uint64_t** table) {
   return AMM_OK;
 }
 
-int amm_exchange_connect_ipc(amm_workspace* ws, const void* ipc_handles) {
-  if (!ws || !ipc_handles || ws->xworld < 2) return AMM_ERR_ARG;
+int amm_device_uuid(int device, void* uuid_out) {
+  if (!uuid_out) return AMM_ERR_ARG;
+  cudaDeviceProp prop;
+  AMM_CUDA(cudaGetDeviceProperties(&prop, device));
+  static_assert(sizeof(prop.uuid) == 16, "GPU UUIDs travel as 16 bytes");
+  memcpy(uuid_out, &prop.uuid, 16);
+  return AMM_OK;
+}
+
+int amm_exchange_connect_ipc(amm_workspace* ws, const void* ipc_handles, const void* device_ids) {
+  if (!ws || !ipc_handles || ws->xworld < 2 || !ws->xbuf) return AMM_ERR_ARG;
+  // Two ranks on ONE GPU (MPS, time slicing, a mis-set CUDA_VISIBLE_DEVICES) would have their
+  // kernels spin-wait for each other on the same device: refuse, the caller falls back to NCCL.
+  if (device_ids) {
+    const unsigned char* ids = (const unsigned char*)device_ids;
+    for (int a = 0; a < ws->xworld; ++a)
+      for (int b = a + 1; b < ws->xworld; ++b)
+        if (memcmp(ids + 16 * a, ids + 16 * b, 16) == 0) return AMM_ERR_ARG;
+  }
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
   uint64_t* table[XCHG_MAX_WORLD];
@@ -451,11 +530,13 @@ int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2
   // `stream` may be NULL = the default stream OF THE CURRENT DEVICE: make that the workspace's
   DeviceGuard guard(ws->device);
   if (guard.rc) return guard.rc;
-  // The kernel publishes the record into pinned host memory and writes `seq` last (after a
-  // system-scope fence), so the host can pick the answer up by polling that word -- a few
-  // microseconds sooner than cudaStreamSynchronize returns.  The stream is queried now and
-  // then so that a failed launch surfaces as an error instead of a hang; after the poll
-  // budget the call falls back to a blocking synchronize.
+  // The kernel publishes the record into pinned host memory as eight words plus a ninth,
+  // position-sensitive checksum word (publish_record; no system-scope fence: it would cost
+  // microseconds on the PCIe path).  The host accepts the slot once `seq` is this call's and the
+  // checksum matches -- a torn slot is simply polled again -- which is a few microseconds sooner
+  // than cudaStreamSynchronize returns.  The stream is queried now and then so that a failed
+  // launch surfaces as an error instead of a hang; after the poll budget the call falls back to
+  // a blocking synchronize.
   const uint64_t want = ws->seq;
   amm_record r;
   bool seen = false;
@@ -475,7 +556,10 @@ int amm_workspace_wait(amm_workspace* ws, void* stream, int mode, uint64_t out[2
     AMM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     if (!read_host_slot(ws, want, &r)) return AMM_ERR_CUDA;  // record never published
   }
-  if (r.flags & AMM_REC_PEER_TIMEOUT) return AMM_ERR_PEER;
+  if (r.flags & AMM_REC_PEER_TIMEOUT) {
+    ws->xbroken = 1;  // the parity banks are out of step now; amm_exchange_destroy + create again
+    return AMM_ERR_PEER;
+  }
   if (r.flags & AMM_REC_BOUNDS) return AMM_ERR_CUDA;  // debug builds: a load left the input range
   combine(&r, 1, mode, out);
   return AMM_OK;
@@ -612,7 +696,10 @@ static int windows_huge(int dtype, const void* dev_ptr, uint64_t n, const uint64
   AMM_CUDA(cudaMemcpyAsync(dbounds, bounds.data(), sizeof(uint64_t) * bounds.size(),
                            cudaMemcpyHostToDevice, stream));
   const int saved = ws->pipelined;
-  ws->pipelined = 0;  // the first scan must order after whatever produced the data
+  // The first scan is non-pipelined: it waits for whatever produced the data BEFORE it signals
+  // launch_dependents (pdl_entry), so scans 2..N -- pipelined, no wait of their own before their
+  // first load -- cannot start ahead of that producer either, even one that triggers early.
+  ws->pipelined = 0;
   int rc = AMM_OK;
   for (uint64_t w = 0; w < n_windows && rc == AMM_OK; ++w) {
     const uint64_t b = bounds[w], e = bounds[n_windows + w];
@@ -900,6 +987,16 @@ int amm_measure_call_latency(int dtype, const void* dev_ptr, uint64_t n, int mod
   return AMM_OK;
 }
 
+/* AMM_PHASE_STAMPS builds only (tools/phase_stamps.py): copies the %globaltimer stamps of the
+   most recent scan, 8 words per CTA, for `ctas` CTAs.  Other builds: AMM_ERR_ARG. */
+int amm_debug_read_stamps(amm_workspace* ws, uint64_t* out, int ctas) {
+  if (!ws || !out || ctas < 1 || !ws->stamps || ctas > ws->max_grid) return AMM_ERR_ARG;
+  DeviceGuard guard(ws->device);
+  if (guard.rc) return guard.rc;
+  AMM_CUDA(cudaMemcpy(out, ws->stamps, (size_t)ctas * 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return AMM_OK;
+}
+
 const char* amm_status_string(int status) {
   switch (status) {
     case AMM_OK: return "ok";
@@ -909,7 +1006,7 @@ const char* amm_status_string(int status) {
     case AMM_ERR_CUDA: return "CUDA error (see amm_last_cuda_error)";
     case AMM_ERR_NCCL: return "NCCL error or NCCL unavailable";
     case AMM_ERR_TOO_LARGE: return "input too large";
-    case AMM_ERR_PEER: return "peer exchange timed out (a rank did not take part in the call)";
+    case AMM_ERR_PEER: return "peer exchange failed (a rank did not take part in the call in time; re-create the exchange)";
     default: return "unknown status";
   }
 }

@@ -34,6 +34,7 @@
 
 #include "../../include/argminmax_b200.h"
 #include "policies.cuh"
+#include "record_slot.h"
 
 namespace amm {
 
@@ -49,8 +50,13 @@ struct ScanParams {
   uint64_t head_elems;     // elements before the first VEC-aligned address (<= n)
   uint64_t n_vec;          // whole vectors in the aligned main region
   uint64_t tail_start;     // first element after the main region
-  uint32_t n_full_tiles;   // n_vec / (blockDim.x * U)
+  uint32_t n_full_tiles;   // statically assigned full tiles: n_vec / (blockDim.x * U) - dyn_tiles
   uint32_t rem_vecs;       // n_vec % (blockDim.x * U)
+  uint64_t per_vecs;       // contiguous partition: vectors per CTA (a multiple of blockDim.x); 0 = grid-stride tiles
+  uint32_t direct_vpt;     // latency kernel: vectors per thread (1..4)
+  uint32_t rem_owner;      // grid-stride tiles: the CTA that takes the partial tile
+  uint32_t dyn_tiles;      // full tiles behind the static ones that CTAs claim at run time (0 = none)
+  uint32_t dyn_koff;       // slot tile ids >= dyn_koff name claimed tiles (UINT32_MAX = none)
   void* partials;          // gridDim.x x Best<Key>
   uint32_t* ticket;        // zero-initialised, self-resetting (atomicInc wrap)
   amm_record* rec_dev;     // device record slot
@@ -64,6 +70,8 @@ struct ScanParams {
   int rank;                    // this GPU's position (ascending shard order)
   uint64_t* const* peer_slots;  // device array [world]: every rank's exchange buffer, peer-mapped
   uint64_t xseq;               // exchange sequence number, identical on all ranks
+  uint64_t xtimeout_ns;        // give up waiting for a peer after this long (0 = wait for ever)
+  uint64_t* stamps;            // AMM_PHASE_STAMPS builds: gridDim.x x 8 %globaltimer stamps (else unused)
 };
 
 // Debug builds (-DAMM_BOUNDS_CHECK, argminmax_b200/_build.py:build_boundscheck) verify that every global load of input
@@ -87,9 +95,24 @@ struct Bounds {
 };
 constexpr uint64_t AMM_REC_BOUNDS = 8ull;  // record.flags bit (debug builds only)
 
-constexpr int XCHG_SLOT_WORDS = 16;     // 128 B per (parity, rank) slot: 8 record words,
-constexpr int XCHG_MAX_WORLD = 16;      // checksum, tag; 2 parities per buffer
-constexpr uint64_t AMM_REC_PEER_TIMEOUT = 4ull;  // record.flags bit: a peer never showed up
+// Phase stamps (-DAMM_PHASE_STAMPS, argminmax_b200/_build.py:build_stamps; tools/phase_stamps.py):
+// thread 0 of every CTA records %globaltimer at the phase boundaries of the scan, so that the
+// fixed cost of a call can be attributed (profiles/r02_fixed_cost.md).  Compiled out otherwise.
+enum : int { ST_ENTRY = 0, ST_FIRST_FOLD = 1, ST_STREAM_DONE = 2, ST_CTA_REDUCED = 3, ST_TICKET = 4,
+             ST_GRID_FOLDED = 5, ST_EXACT_DONE = 6, ST_PUBLISHED = 7 };
+__device__ __forceinline__ void stamp(const ScanParams& p, int which) {
+#ifdef AMM_PHASE_STAMPS
+  if (p.stamps != nullptr && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.stamps[(uint64_t)blockIdx.x * 8 + which] = t;
+  }
+#else
+  (void)p;
+  (void)which;
+#endif
+}
+
 
 // (key, position) candidates for min, max and first NaN.  Positions are global vector
 // indices in the streaming phase and element indices in the exact phase.
@@ -294,12 +317,10 @@ __device__ __forceinline__ typename P::Elem vec_elem(const uint32_t (&w)[NW], in
 // The host polls the pinned slot.  Instead of ordering the eight words with a system-scope
 // fence (which costs microseconds on the PCIe path), a ninth word carries a checksum over
 // the other eight: the host accepts the slot only when `seq` matches the call AND the
-// checksum matches, so a torn / partially arrived record is simply polled again.
-__device__ __forceinline__ uint64_t record_checksum(const amm_record& r) {
-  return r.min_key ^ r.min_idx ^ r.max_key ^ r.max_idx ^ r.nan_idx ^ r.flags ^ r.n ^ r.seq ^
-         0xA5A5C3C3F00DBEEFull;
-}
-
+// checksum matches, so a torn / partially arrived record is simply polled again.  The
+// checksum is position-sensitive (multiply-rotate per word, seeded): a slot that mixes 16-byte
+// pairs of two different records does not pass by accident the way a plain XOR would when the
+// stale words happen to cancel (small integer keys and indices do that).
 __device__ __forceinline__ void publish_record(const ScanParams& p, const amm_record& r) {
   *p.rec_dev = r;
   if (p.rec_host != nullptr) {
@@ -314,7 +335,8 @@ __device__ __forceinline__ void publish_record(const ScanParams& p, const amm_re
       asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(h + 2 * i), "l"(w[2 * i]),
                    "l"(w[2 * i + 1])
                    : "memory");
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(h + 8), "l"(record_checksum(r)) : "memory");
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(h + 8), "l"(mix_checksum(w, HOST_SLOT_SEED))
+                 : "memory");
     if (p.publish_fence) __threadfence_system();
   }
 }
@@ -338,85 +360,96 @@ __device__ __forceinline__ amm_record make_record(const ScanParams& p, const Bes
   return r;
 }
 
-// Last step of the last CTA.  world == 1: publish this GPU's record.  world > 1: the
-// compute step is FUSED with its collective -- instead of returning to the host for an NCCL
-// all-gather, the last CTA stores its 64-byte record straight into every peer's exchange
-// buffer over NVLink (peer-mapped pointers, one thread per peer), then polls its own buffer
-// until all `world` records of this call (tag == xseq, checksum valid) have landed, folds them
-// in ascending rank order with strict compares (= global first occurrence, the reference's
-// merge rule src/simd/generic.rs:513-520) and publishes the GLOBAL record.  Two parity banks
-// make back-to-back calls safe: a rank can only reach call s+2 after every peer has finished
-// reading call s.  A peer that never arrives trips a ~4 s timeout and is reported in flags.
+// Last step of a call, executed by WARP 0 of the last CTA (all 32 lanes must call; `x` is read
+// from lane 0).  world == 1: publish this GPU's record.  world > 1: the compute step is FUSED
+// with its collective -- instead of returning to the host for an NCCL all-gather, lane t stores
+// the 64-byte record straight into peer t's exchange buffer over NVLink (peer-mapped pointers),
+// then polls this GPU's own buffer until peer t's record of this call (tag == xseq, checksum
+// valid) has landed; lane 0 folds the `world` records in ascending rank order with strict
+// compares (= global first occurrence, the reference's merge rule src/simd/generic.rs:513-520)
+// and publishes the GLOBAL record.  Two parity banks make back-to-back calls safe: a rank can
+// only reach call s+2 after every peer has finished reading call s.
+// A peer that does not arrive within xtimeout_ns (0 = wait for ever) makes the failure
+// COLLECTIVE: the waiting rank re-pushes its own record with AMM_REC_PEER_TIMEOUT set into every
+// peer's buffer, so a late rank that would otherwise have completed normally reads the flag and
+// fails too; the host layer then marks the exchange unusable (libamm.cu: amm_workspace_wait).
 // XCHG is a compile-time flag of the kernels: single-GPU launches use instantiations that do
 // not contain this code at all (its mere presence costs the streaming loop ~3 % -- registers,
 // loss of uniform-datapath loop control), multi-GPU launches use the fused instantiations.
+__device__ __forceinline__ void push_peer_slot(volatile uint64_t* dst, const uint64_t* src /* [8] */,
+                                               uint64_t xseq) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dst[i] = src[i];
+  dst[8] = mix_checksum(src, PEER_SLOT_SEED ^ xseq);
+  dst[9] = xseq;
+}
+
 template <typename Key>
-__device__ __forceinline__ void exchange_and_publish(const ScanParams& p, const Best<Key>& x) {
+__device__ __forceinline__ void exchange_and_publish_warp(const ScanParams& p, const Best<Key>& x) {
   __shared__ amm_record s_mine;
   __shared__ amm_record s_all[XCHG_MAX_WORLD];
   __shared__ uint32_t s_timeout;
-  if (threadIdx.x == 0) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) {
     s_mine = make_record(p, x);
     s_timeout = 0;
   }
-  __syncthreads();
+  __syncwarp();
   const uint64_t bank = (p.xseq & 1ull) * (uint64_t)p.world;
-  if ((int)threadIdx.x < p.world) {
-    // push my record into peer `t`'s buffer, slot [bank + rank]
-    const int t = threadIdx.x;
-    volatile uint64_t* dst = p.peer_slots[t] + (bank + (uint64_t)p.rank) * XCHG_SLOT_WORDS;
-    const uint64_t* src = reinterpret_cast<const uint64_t*>(&s_mine);
-    uint64_t c = 0x5EEDFACE0DDBA11ull ^ p.xseq;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      dst[i] = src[i];
-      c ^= src[i];
-    }
-    dst[8] = c;
-    dst[9] = p.xseq;
+  const bool active = lane < p.world;
+  if (active) {
+    // push my record into peer `lane`'s buffer, slot [bank + rank]
+    volatile uint64_t* dst = p.peer_slots[lane] + (bank + (uint64_t)p.rank) * XCHG_SLOT_WORDS;
+    push_peer_slot(dst, reinterpret_cast<const uint64_t*>(&s_mine), p.xseq);
     __threadfence_system();
-    // pull peer `t`'s record out of MY buffer, slot [bank + t]
-    const volatile uint64_t* in = p.peer_slots[p.rank] + (bank + (uint64_t)t) * XCHG_SLOT_WORDS;
+    // pull peer `lane`'s record out of MY buffer, slot [bank + lane]
+    const volatile uint64_t* in = p.peer_slots[p.rank] + (bank + (uint64_t)lane) * XCHG_SLOT_WORDS;
     uint64_t w[10];
     unsigned long long t0 = 0, now = 0;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     bool ok = false;
+    uint32_t spins = 0;
     while (!ok) {
       if (in[9] == p.xseq) {
 #pragma unroll
         for (int i = 0; i < 10; ++i) w[i] = in[i];
-        uint64_t cc = 0x5EEDFACE0DDBA11ull ^ p.xseq;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) cc ^= w[i];
-        ok = (cc == w[8]) && (w[9] == p.xseq);
+        ok = (mix_checksum(w, PEER_SLOT_SEED ^ p.xseq) == w[8]) && (w[9] == p.xseq);
       }
-      if (!ok) {
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
-        if (now - t0 > 4000000000ull) {  // ns
+      if (!ok && p.xtimeout_ns != 0 && (++spins & 0x3Fu) == 0) {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > p.xtimeout_ns) {
           atomicExch(&s_timeout, 1u);
           break;
         }
       }
     }
-    uint64_t* out = reinterpret_cast<uint64_t*>(&s_all[t]);
-    if (ok) {
+    uint64_t* out = reinterpret_cast<uint64_t*>(&s_all[lane]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) out[i] = w[i];
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) out[i] = 0;  // no value, no NaN
+    for (int i = 0; i < 8; ++i) out[i] = ok ? w[i] : 0ull;  // not arrived: no value, no NaN
+  }
+  __syncwarp();
+  if (s_timeout != 0) {  // warp-uniform
+    // collective failure: poison my slot in every peer's buffer (same call, flag set)
+    if (lane == 0) s_mine.flags |= AMM_REC_PEER_TIMEOUT;
+    __syncwarp();
+    if (active) {
+      volatile uint64_t* dst = p.peer_slots[lane] + (bank + (uint64_t)p.rank) * XCHG_SLOT_WORDS;
+      push_peer_slot(dst, reinterpret_cast<const uint64_t*>(&s_mine), p.xseq);
+      __threadfence_system();
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  __syncwarp();
+  if (lane == 0) {
     amm_record o;
     bool have = false;
     o.min_key = o.max_key = 0;
     o.min_idx = o.max_idx = o.nan_idx = AMM_NO_INDEX;
     o.n = 0;
+    uint64_t bad = s_timeout ? AMM_REC_PEER_TIMEOUT : 0ull;
     for (int g = 0; g < p.world; ++g) {
       const amm_record r = s_all[g];
       o.n += r.n;
+      bad |= r.flags & AMM_REC_PEER_TIMEOUT;  // a peer gave up on this call
       if ((r.flags & AMM_REC_HAS_NAN) && r.nan_idx < o.nan_idx) o.nan_idx = r.nan_idx;
       if (!(r.flags & AMM_REC_HAS_VALUE)) continue;
       if (!have || r.min_key < o.min_key || (r.min_key == o.min_key && r.min_idx < o.min_idx)) {
@@ -430,35 +463,47 @@ __device__ __forceinline__ void exchange_and_publish(const ScanParams& p, const 
       have = true;
     }
     o.flags = (have ? AMM_REC_HAS_VALUE : 0ull) |
-              (o.nan_idx != AMM_NO_INDEX ? AMM_REC_HAS_NAN : 0ull) |
-              (s_timeout ? AMM_REC_PEER_TIMEOUT : 0ull);
+              (o.nan_idx != AMM_NO_INDEX ? AMM_REC_HAS_NAN : 0ull) | bad;
     o.seq = p.seq;
     publish_record(p, o);
   }
 }
 
 template <bool XCHG, typename Key>
-__device__ __forceinline__ void finalize(const ScanParams& p, const Best<Key>& x) {
+__device__ __forceinline__ void finalize_warp(const ScanParams& p, const Best<Key>& x) {
   if (XCHG) {
-    exchange_and_publish(p, x);
+    exchange_and_publish_warp(p, x);
   } else {
-    if (threadIdx.x == 0) publish_record(p, make_record(p, x));
+    if ((threadIdx.x & 31) == 0) publish_record(p, make_record(p, x));
   }
+  stamp(p, ST_PUBLISHED);
 }
 
 // Programmatic dependent launch (PDL).  Scans are launched with the programmatic-stream-
-// serialization attribute and every CTA signals launch_dependents on entry, so the NEXT scan
-// on the stream can be scheduled while this one drains.  Default (safe) mode: a CTA executes
-// griddepcontrol.wait before its first global load, i.e. only launch latency is hidden.
+// serialization attribute, so the NEXT scan on the stream can be scheduled while this one drains.
+// Default (safe) mode: a CTA executes griddepcontrol.wait before its first global load and only
+// then signals launch_dependents -- launch latency is hidden, and because the trigger comes after
+// the wait a dependent can never run ahead of the kernel that produced THIS scan's input (a
+// PDL-aware producer that triggers early is therefore harmless, also for a pipelined scan that
+// follows a non-pipelined one, as in windows_huge).
 // Pipelined mode (amm_workspace_set_pipelined, caller promises that a scan's input is not
-// produced by the kernel right before it on the stream): the wait moves to the point where
-// the CTA first touches the shared workspace (partials, ticket, record slots), so the
-// STREAMING phase of scan k+1 overlaps the fold / locate / publish tail of scan k.
+// produced by the kernel right before it on the stream): the trigger is issued on entry and the
+// wait moves to the point where the CTA first touches the shared workspace (partials, ticket,
+// record slots), so the STREAMING phase of scan k+1 overlaps the fold / locate / publish tail
+// of scan k.
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 __device__ __forceinline__ void pdl_wait_prior_grid() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_entry(const ScanParams& p) {
+  if (p.pipelined) {
+    pdl_launch_dependents();
+  } else {
+    pdl_wait_prior_grid();
+    pdl_launch_dependents();
+  }
 }
 
 // Cross-CTA reduce: every CTA deposits its Best, the last one to arrive (ticket) folds them.
@@ -476,6 +521,7 @@ __device__ __forceinline__ bool grid_reduce(const ScanParams& p, Best<Key>& b, B
     const uint32_t ticket = atomicInc(p.ticket, gridDim.x - 1);  // wraps to 0: reusable
     *s_is_last = (ticket == gridDim.x - 1);
   }
+  stamp(p, ST_TICKET);
   __syncthreads();
   if (!*s_is_last) return false;
   __threadfence();
@@ -496,345 +542,322 @@ __device__ __forceinline__ bool grid_reduce(const ScanParams& p, Best<Key>& b, B
 }
 
 // ---------------------------------------------------------------------------------------
-// Small inputs (a few MB): latency, not bandwidth, is what a caller sees.  One pass with
-// exact per-element (key, index) tracking -- no tile bookkeeping, no second phase: each CTA
-// takes a contiguous slice, CTA reduce, ticket, the last CTA folds the partials and
-// publishes.  The dependent chain is load -> reduce -> ticket -> fold -> publish.
+// Cross-CTA step for 32-bit keys and fewer than 2^32 - 2 positions: a candidate is ONE 64-bit
+// word, (biased key << 32) | position for the minimum and (biased key << 32) | ~position for the
+// maximum, so "smaller key, then smaller position" is a plain unsigned min and "larger key, then
+// smaller position" a plain unsigned max.  Every CTA folds its word into the workspace with one
+// atomicMin / atomicMax (+ one for the first NaN position) and takes a ticket; the last CTA swaps
+// the words back to their identities and carries on.  Compared with "store partials, ticket, last
+// CTA loads and reduces them" this removes one global round trip and one CTA-wide reduce from the
+// dependent chain (tools/exp/latency_floor.cu: 9.4 -> 8.1 us for the skeleton of a 4 MiB scan).
+// Positions are element indices in the latency kernel and vector indices in the streaming
+// kernel.  Words: p.ticket + 16 (min), + 18 (max), + 20 (NaN).
 // ---------------------------------------------------------------------------------------
-// Cross-CTA step of the latency kernel for 32-bit keys and fewer than 2^32 - 2 elements: a
-// candidate is ONE 64-bit word, (biased key << 32) | index for the minimum and
-// (biased key << 32) | ~index for the maximum, so "smaller key, then smaller index" is a plain
-// unsigned min and "larger key, then smaller index" a plain unsigned max.  Every CTA folds its
-// word into the workspace with one atomicMin / atomicMax (+ one for the first NaN index) and takes
-// a ticket; the last CTA swaps the words back to their identities and publishes.  Compared with
-// "store partials, ticket, last CTA loads and reduces them" this removes one global round trip
-// and one CTA-wide reduce from the dependent chain (tools/exp/latency_floor.cu: 9.4 -> 8.1 us
-// for the skeleton of a 4 MiB scan).  Words: p.ticket + 16 (min), + 18 (max), + 20 (NaN).
 constexpr unsigned long long PACK_MIN_NONE = ~0ull;
 constexpr unsigned long long PACK_MAX_NONE = 0ull;
-__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
-  return __shfl_xor_sync(0xFFFFFFFFu, v, m);
-}
-struct PackedWords {
-  unsigned long long wmin, wmax, wnan;
+constexpr uint32_t PACK_POS_NONE = 0xFFFFFFFFu;
+
+// One thread's / warp's / CTA's candidates in 32-bit pieces: keys BIASED (key ^ 0x80000000, so
+// unsigned order is key order), 32-bit positions, PACK_POS_NONE = nothing yet.  Reduced with the
+// warp-wide integer min/max instruction (redux.sync, 5 instructions per level instead of 5
+// shuffle rounds over three 64-bit words).
+struct PackedCand {
+  uint32_t kmin, pmin, kmax, pmax, pnan;
   __device__ __forceinline__ void clear() {
-    wmin = PACK_MIN_NONE;
-    wmax = PACK_MAX_NONE;
-    wnan = POS_NONE;
+    kmin = 0xFFFFFFFFu;
+    kmax = 0u;
+    pmin = pmax = pnan = PACK_POS_NONE;
   }
-  __device__ __forceinline__ void set_min(int32_t key, uint32_t pos) {
-    wmin = ((unsigned long long)((uint32_t)key ^ 0x80000000u) << 32) | pos;
+  __device__ __forceinline__ void set(int32_t key_min, uint32_t pos_min, int32_t key_max, uint32_t pos_max) {
+    kmin = (uint32_t)key_min ^ 0x80000000u;
+    pmin = pos_min;
+    kmax = (uint32_t)key_max ^ 0x80000000u;
+    pmax = pos_max;
   }
-  __device__ __forceinline__ void set_max(int32_t key, uint32_t pos) {
-    wmax = ((unsigned long long)((uint32_t)key ^ 0x80000000u) << 32) | (uint32_t)~pos;
+  template <bool TRACK_NAN>
+  __device__ __forceinline__ void warp_reduce() {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const bool has = pmin != PACK_POS_NONE;  // pmin and pmax are set together
+    const uint32_t km = __reduce_min_sync(FULL, has ? kmin : 0xFFFFFFFFu);
+    const uint32_t kM = __reduce_max_sync(FULL, has ? kmax : 0u);
+    const uint32_t pm = __reduce_min_sync(FULL, (has && kmin == km) ? pmin : PACK_POS_NONE);
+    const uint32_t pM = __reduce_min_sync(FULL, (has && kmax == kM) ? pmax : PACK_POS_NONE);
+    kmin = km;
+    kmax = kM;
+    pmin = pm;
+    pmax = pM;
+    if (TRACK_NAN) pnan = __reduce_min_sync(FULL, pnan);
   }
-  // -> Best with 32-bit positions widened
+  // -> Best with positions widened
   __device__ __forceinline__ Best<int32_t> unpack() const {
     Best<int32_t> g;
     g.clear();
-    if (wmin != PACK_MIN_NONE) {
-      g.kmin = (int32_t)((uint32_t)(wmin >> 32) ^ 0x80000000u);
-      g.pmin = (uint32_t)wmin;
+    if (pmin != PACK_POS_NONE) {
+      g.kmin = (int32_t)(kmin ^ 0x80000000u);
+      g.pmin = pmin;
+      g.kmax = (int32_t)(kmax ^ 0x80000000u);
+      g.pmax = pmax;
     }
-    if (wmax != PACK_MAX_NONE) {
-      g.kmax = (int32_t)((uint32_t)(wmax >> 32) ^ 0x80000000u);
-      g.pmax = (uint32_t)~(uint32_t)wmax;
-    }
-    g.pnan = wnan;
+    if (pnan != PACK_POS_NONE) g.pnan = pnan;
     return g;
   }
 };
 
-// Folds every thread's words over the CTA and then over the grid.  Returns true in ALL lanes of
-// warp 0 of the last CTA to arrive (or of the only CTA), with the grid-wide words in `w`; every
-// other thread gets false.  All threads of the CTA must call (one __syncthreads inside).
+// Folds every thread's candidates over the CTA and then over the grid.  Returns true in ALL lanes
+// of warp 0 of the last CTA to arrive (or of the only CTA), with the grid-wide candidates in `c`;
+// every other thread gets false.  All threads of the CTA must call (one __syncthreads inside).
 template <class P>
-__device__ __forceinline__ bool packed_grid_reduce(const ScanParams& p, PackedWords& w,
-                                                   unsigned long long* smem /* [3][32] */) {
-  auto warp_fold = [&]() {
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      const unsigned long long a = shfl_xor_u64(w.wmin, m), b = shfl_xor_u64(w.wmax, m);
-      w.wmin = a < w.wmin ? a : w.wmin;
-      w.wmax = b > w.wmax ? b : w.wmax;
-      if (P::TRACK_NAN) {
-        const unsigned long long c = shfl_xor_u64(w.wnan, m);
-        w.wnan = c < w.wnan ? c : w.wnan;
-      }
-    }
-  };
-  warp_fold();
+__device__ __forceinline__ bool packed_grid_reduce(const ScanParams& p, PackedCand& c,
+                                                   uint32_t* smem /* [5][32] */) {
+  c.warp_reduce<P::TRACK_NAN>();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = (blockDim.x + 31) >> 5;
-  if (lane == 0) {
-    smem[warp] = w.wmin;
-    smem[32 + warp] = w.wmax;
-    if (P::TRACK_NAN) smem[64 + warp] = w.wnan;
+  if (nwarps > 1) {
+    if (lane == 0) {
+      smem[warp] = c.kmin;
+      smem[32 + warp] = c.pmin;
+      smem[64 + warp] = c.kmax;
+      smem[96 + warp] = c.pmax;
+      if (P::TRACK_NAN) smem[128 + warp] = c.pnan;
+    }
+    __syncthreads();
+    if (warp != 0) return false;
+    c.clear();
+    if (lane < nwarps) {
+      c.kmin = smem[lane];
+      c.pmin = smem[32 + lane];
+      c.kmax = smem[64 + lane];
+      c.pmax = smem[96 + lane];
+      if (P::TRACK_NAN) c.pnan = smem[128 + lane];
+    }
+    c.warp_reduce<P::TRACK_NAN>();
   }
-  __syncthreads();
-  if (warp != 0) return false;
-  w.wmin = lane < nwarps ? smem[lane] : PACK_MIN_NONE;
-  w.wmax = lane < nwarps ? smem[32 + lane] : PACK_MAX_NONE;
-  w.wnan = (P::TRACK_NAN && lane < nwarps) ? smem[64 + lane] : POS_NONE;
-  warp_fold();
+  stamp(p, ST_CTA_REDUCED);
   uint32_t last = 1;
+  unsigned long long wmin = PACK_MIN_NONE, wmax = PACK_MAX_NONE, wnan = POS_NONE;
   if (lane == 0) {
     pdl_wait_prior_grid();  // from here on the workspace is ours
     if (gridDim.x > 1) {
       unsigned long long* words = reinterpret_cast<unsigned long long*>(p.ticket + 16);
-      if (w.wmin != PACK_MIN_NONE) atomicMin(&words[0], w.wmin);
-      if (w.wmax != PACK_MAX_NONE) atomicMax(&words[1], w.wmax);
-      if (P::TRACK_NAN && w.wnan != POS_NONE) atomicMin(&words[2], w.wnan);
+      if (c.pmin != PACK_POS_NONE) {
+        atomicMin(&words[0], ((unsigned long long)c.kmin << 32) | c.pmin);
+        atomicMax(&words[1], ((unsigned long long)c.kmax << 32) | (uint32_t)~c.pmax);
+      }
+      if (P::TRACK_NAN && c.pnan != PACK_POS_NONE) atomicMin(&words[2], (unsigned long long)c.pnan);
       __threadfence();
       last = atomicInc(p.ticket, gridDim.x - 1) == gridDim.x - 1;
       if (last) {
         __threadfence();
-        w.wmin = atomicExch(&words[0], PACK_MIN_NONE);  // read the grid-wide result and re-arm
-        w.wmax = atomicExch(&words[1], PACK_MAX_NONE);
-        if (P::TRACK_NAN) w.wnan = atomicExch(&words[2], POS_NONE);
+        wmin = atomicExch(&words[0], PACK_MIN_NONE);  // read the grid-wide result and re-arm
+        wmax = atomicExch(&words[1], PACK_MAX_NONE);
+        if (P::TRACK_NAN) wnan = atomicExch(&words[2], POS_NONE);
       }
     }
   }
+  stamp(p, ST_TICKET);
   last = __shfl_sync(0xFFFFFFFFu, last, 0);
   if (!last) return false;
-  w.wmin = __shfl_sync(0xFFFFFFFFu, w.wmin, 0);
-  w.wmax = __shfl_sync(0xFFFFFFFFu, w.wmax, 0);
-  w.wnan = __shfl_sync(0xFFFFFFFFu, w.wnan, 0);
+  if (gridDim.x > 1) {
+    wmin = __shfl_sync(0xFFFFFFFFu, wmin, 0);
+    wmax = __shfl_sync(0xFFFFFFFFu, wmax, 0);
+    wnan = __shfl_sync(0xFFFFFFFFu, wnan, 0);
+    c.clear();
+    if (wmin != PACK_MIN_NONE) {
+      c.kmin = (uint32_t)(wmin >> 32);
+      c.pmin = (uint32_t)wmin;
+      c.kmax = (uint32_t)(wmax >> 32);
+      c.pmax = ~(uint32_t)wmax;
+    }
+    c.pnan = (wnan == POS_NONE) ? PACK_POS_NONE : (uint32_t)wnan;
+  }
   return true;
 }
 
+// Shared-memory scratch of the cross-CTA step: Best<Key>[32] for the partials flow, 5 x 32 words
+// for the packed flow.
+template <typename Key>
+struct alignas(16) ReduceScratch {
+  static constexpr size_t BYTES = sizeof(Best<Key>) * 32 > 640 ? sizeof(Best<Key>) * 32 : 640;
+  unsigned char raw[BYTES];
+  __device__ __forceinline__ Best<Key>* best() { return reinterpret_cast<Best<Key>*>(raw); }
+  __device__ __forceinline__ uint32_t* words() { return reinterpret_cast<uint32_t*>(raw); }
+};
+
+// ---------------------------------------------------------------------------------------
+// Small inputs (up to a few MB): latency, not bandwidth, is what a caller sees.  ONE trip: every
+// thread loads its 1..4 vectors (16 B each, `direct_vpt` per thread, all in flight at once) and
+// keeps them in registers; value-only fold per vector exactly as in the streaming kernel, the
+// best vector per direction is remembered by its register slot, and the first matching element is
+// then located IN REGISTERS -- no index is carried per element and nothing is re-read.  The
+// dependent chain is load -> fold + locate -> CTA reduce -> grid step -> publish.
+// ---------------------------------------------------------------------------------------
 template <class P, bool XCHG, bool PACKED = false>
 __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const ScanParams p) {
   using Key = typename P::Key;
+  using Elem = typename P::Elem;
   constexpr int VEC = 16, NW = 4, UN = 4;
-  constexpr int VE = VEC / sizeof(typename P::Elem);
-  __shared__ Best<Key> smem[32];
+  constexpr int VE = VEC / sizeof(Elem);
+  __shared__ ReduceScratch<Key> scratch;
   __shared__ uint32_t s_is_last;
-  pdl_launch_dependents();
-  if (!p.pipelined) pdl_wait_prior_grid();
-  const uint8_t* main_base = p.base + p.head_elems * sizeof(typename P::Elem);
+  pdl_entry(p);
+  stamp(p, ST_ENTRY);
+  const uint8_t* main_base = p.base + p.head_elems * sizeof(Elem);
   const Bounds bd(p);
-  // contiguous slice of whole vectors per CTA, coalesced 128-bit loads, UN in flight
-  const uint64_t per = (p.n_vec + gridDim.x - 1) / gridDim.x;
-  const uint64_t vb = per * blockIdx.x;
-  uint64_t ve = vb + per;
-  ve = ve < p.n_vec ? ve : p.n_vec;
+  const uint32_t vpt = p.direct_vpt;  // vectors per thread, 1..UN
+  const uint64_t v0 = (uint64_t)blockIdx.x * blockDim.x * vpt + threadIdx.x;
+  uint32_t w[UN][NW];
+  bool have[UN];
+#pragma unroll
+  for (int u = 0; u < UN; ++u) {
+    const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
+    have[u] = (uint32_t)u < vpt && vi < p.n_vec;
+    if (have[u]) {
+      bd.check(main_base + vi * VEC, VEC);
+      VecLoad<VEC>::ld(main_base + vi * VEC, w[u]);
+    }
+  }
+  // value-only fold per vector; vectors ascend with u, so a strict compare keeps the first
+  Key bkmin = KeyLim<Key>::MAXV, bkmax = KeyLim<Key>::MINV;
+  int umin = -1, umax = -1, unan = -1;
+#pragma unroll
+  for (int u = 0; u < UN; ++u) {
+    if (have[u]) {
+      typename P::Acc acc;
+      P::init(acc, &w[u][0]);
+#pragma unroll
+      for (int q = P::WPI; q < NW; q += P::WPI) P::feed(acc, &w[u][q]);
+      Key kmin, kmax;
+      bool valid, has_nan;
+      P::finish(acc, kmin, kmax, valid, has_nan);
+      const bool um = valid && (umin < 0 || kmin < bkmin);
+      const bool uM = valid && (umax < 0 || kmax > bkmax);
+      bkmin = um ? kmin : bkmin;
+      umin = um ? u : umin;
+      bkmax = uM ? kmax : bkmax;
+      umax = uM ? u : umax;
+      if (P::TRACK_NAN) unan = (has_nan && unan < 0) ? u : unan;
+    }
+  }
+  stamp(p, ST_FIRST_FOLD);
+  // locate the first matching element inside the winning vectors (registers only)
   Best<Key> x;
   x.clear();
-  for (uint64_t v0 = vb + threadIdx.x; v0 < ve; v0 += (uint64_t)UN * blockDim.x) {
-    uint32_t w[UN][NW];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
-      if (vi < ve) {
-        bd.check(main_base + vi * VEC, VEC);
-        VecLoad<VEC>::ld(main_base + vi * VEC, w[u]);
+  for (int u = 0; u < UN; ++u) {
+    const bool is_min = (u == umin), is_max = (u == umax), is_nan = P::TRACK_NAN && (u == unan);
+    if (is_min || is_max || is_nan) {
+      int emin = VE, emax = VE, enan = VE;
+#pragma unroll
+      for (int e = VE - 1; e >= 0; --e) {
+        Key k;
+        bool valid, nan;
+        P::classify(vec_elem<P, NW>(w[u], e), k, valid, nan);
+        emin = (valid && k == bkmin) ? e : emin;
+        emax = (valid && k == bkmax) ? e : emax;
+        if (P::TRACK_NAN) enan = nan ? e : enan;
       }
-    }
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const uint64_t vi = v0 + (uint64_t)u * blockDim.x;
-      if (vi < ve) {
-        const uint64_t i0 = p.head_elems + vi * VE;
-#pragma unroll
-        for (int e = 0; e < VE; ++e) {
-          Key k;
-          bool valid, is_nan;
-          P::classify(vec_elem<P, NW>(w[u], e), k, valid, is_nan);
-          // indices ascend within a thread: a strict compare keeps the first occurrence
-          if (valid && (k < x.kmin || x.pmin == POS_NONE)) {
-            x.kmin = k;
-            x.pmin = i0 + e;
-          }
-          if (valid && (k > x.kmax || x.pmax == POS_NONE)) {
-            x.kmax = k;
-            x.pmax = i0 + e;
-          }
-          if (P::TRACK_NAN && is_nan && x.pnan == POS_NONE) x.pnan = i0 + e;
-        }
+      const uint64_t i0 = p.head_elems + (v0 + (uint64_t)u * blockDim.x) * VE;
+      if (is_min) {
+        x.kmin = bkmin;
+        x.pmin = i0 + emin;
       }
+      if (is_max) {
+        x.kmax = bkmax;
+        x.pmax = i0 + emax;
+      }
+      if (is_nan) x.pnan = i0 + enan;
     }
   }
   // unaligned head / sub-vector tail (< 16 B each): lexicographic merges, any order
   if (blockIdx.x == 0) exact_range<P, false>(bd, p.base, 0, p.head_elems, x);
   if (blockIdx.x == gridDim.x - 1) exact_range<P, false>(bd, p.base, p.tail_start, p.n, x);
+  stamp(p, ST_STREAM_DONE);
   if constexpr (PACKED) {
-    static_assert(sizeof(Key) == 4 && !XCHG, "packed candidates need 32-bit keys");
-    PackedWords w;
-    w.clear();
-    if (x.pmin != POS_NONE) w.set_min(x.kmin, (uint32_t)x.pmin);
-    if (x.pmax != POS_NONE) w.set_max(x.kmax, (uint32_t)x.pmax);
-    if (P::TRACK_NAN) w.wnan = x.pnan;
-    if (!packed_grid_reduce<P>(p, w, reinterpret_cast<unsigned long long*>(smem))) return;
-    if (threadIdx.x == 0) publish_record(p, make_record(p, w.unpack()));
+    static_assert(sizeof(Key) == 4, "packed candidates need 32-bit keys");
+    PackedCand c;
+    c.clear();
+    if (x.pmin != POS_NONE) c.set(x.kmin, (uint32_t)x.pmin, x.kmax, (uint32_t)x.pmax);
+    if (P::TRACK_NAN && x.pnan != POS_NONE) c.pnan = (uint32_t)x.pnan;
+    if (!packed_grid_reduce<P>(p, c, scratch.words())) return;
+    stamp(p, ST_GRID_FOLDED);
+    stamp(p, ST_EXACT_DONE);
+    finalize_warp<XCHG>(p, c.unpack());
   } else {
-    x = block_reduce(x, smem);
-    if (!grid_reduce(p, x, smem, &s_is_last)) return;
-    finalize<XCHG>(p, x);
+    x = block_reduce(x, scratch.best());
+    stamp(p, ST_CTA_REDUCED);
+    if (!grid_reduce(p, x, scratch.best(), &s_is_last)) return;
+    if (threadIdx.x >= 32) return;
+    stamp(p, ST_GRID_FOLDED);
+    stamp(p, ST_EXACT_DONE);
+    finalize_warp<XCHG>(p, x);
   }
 }
 
-template <class P, int VEC, int U, bool PREFETCH, int HINT, bool XCHG>
-__global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanParams p) {
-  using VL = VecLoad<VEC, HINT>;
-  constexpr uint32_t VEC_ELEMS = VEC / sizeof(typename P::Elem);
+// ---------------------------------------------------------------------------------------
+// Exact finish, executed by WARP 0 of the last CTA (all 32 lanes; the result is valid in lane 0):
+// the winning min / max / first-NaN vectors (`b` holds their VECTOR indices; <= 32 elements each)
+// are re-read with one element per lane and a ballot picks the first match; the unaligned head
+// and the sub-vector tail (< one vector each) ride along as exact per-lane candidates.  All five
+// loads are issued before the first one is consumed: one memory round trip, not five.
+// ---------------------------------------------------------------------------------------
+template <class P, uint32_t VEC_ELEMS>
+__device__ __forceinline__ Best<typename P::Key> exact_finish_warp(const ScanParams& p, const Bounds& bd,
+                                                                   const Best<typename P::Key>& b) {
+  using Elem = typename P::Elem;
   using Key = typename P::Key;
-  constexpr int NW = VL::NW;
-  __shared__ Best<Key> smem[32];
-  __shared__ uint32_t s_is_last;
-  pdl_launch_dependents();
-  if (!p.pipelined) pdl_wait_prior_grid();
+  static_assert(VEC_ELEMS <= 32, "one element per lane");
+  const Elem* e = reinterpret_cast<const Elem*>(p.base);
+  const uint32_t lane = threadIdx.x & 31;
+  constexpr int NC = P::TRACK_NAN ? 3 : 2;
+  const uint64_t cand[3] = {b.pmin, b.pmax, b.pnan};
+  Elem raw[5];
+  bool have[5];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    have[c] = cand[c] != POS_NONE && lane < VEC_ELEMS;
+    const uint64_t i = p.head_elems + cand[c] * VEC_ELEMS + lane;
+    if (have[c]) bd.check(&e[i], sizeof(Elem));
+    raw[c] = have[c] ? e[i] : Elem(0);
+  }
+  // head: elements [0, head_elems); tail: [tail_start, n); both shorter than one vector
+  const uint64_t ih = lane, it = p.tail_start + lane;
+  have[3] = ih < p.head_elems;
+  have[4] = it < p.n;
+  if (have[3]) bd.check(&e[ih], sizeof(Elem));
+  if (have[4]) bd.check(&e[it], sizeof(Elem));
+  raw[3] = have[3] ? e[ih] : Elem(0);
+  raw[4] = have[4] ? e[it] : Elem(0);
 
-  const uint32_t tile_vecs = blockDim.x * U;
-  const uint64_t tile_bytes = (uint64_t)tile_vecs * VEC;
-  const uint8_t* main_base = p.base + p.head_elems * sizeof(typename P::Elem);
-  const Bounds bd(p);
-
-  Running<Key> run;
-  run.kmin = KeyLim<Key>::MAXV;
-  run.kmax = KeyLim<Key>::MINV;
-  run.smin = run.smax = run.snan = TILE_NONE;
-
-  // ------------------------------------------------ streaming phase: full tiles
-  // Two register buffers in ping-pong: the loads of the next tile are in flight
-  // while the current one is folded (PREFETCH), without register-to-register moves.
-  {
-    const uint32_t nft = p.n_full_tiles;
-    const uint8_t* lane_base = main_base + (uint64_t)threadIdx.x * VEC;
-    const uint64_t jstride = (uint64_t)blockDim.x * VEC;
-    uint32_t t = blockIdx.x;
-    uint32_t a[U][NW];
-    if (PREFETCH) {
-      uint32_t b[U][NW];
-      if (t < nft) {
-        const uint8_t* q = lane_base + (uint64_t)t * tile_bytes;
+  Best<Key> x;
+  x.clear();
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-          bd.check(q + j * jstride, VEC);
-          VL::ld(q + j * jstride, a[j]);
-        }
-      }
-      while (t < nft) {
-        const uint32_t t1 = t + gridDim.x;
-        if (t1 < nft) {
-          const uint8_t* q = lane_base + (uint64_t)t1 * tile_bytes;
-#pragma unroll
-          for (int j = 0; j < U; ++j) {
-            bd.check(q + j * jstride, VEC);
-            VL::ld(q + j * jstride, b[j]);
-          }
-        }
-        fold_tile<P, NW, U>(a, t, run);
-        if (t1 >= nft) break;
-        const uint32_t t2 = t1 + gridDim.x;
-        if (t2 < nft) {
-          const uint8_t* q = lane_base + (uint64_t)t2 * tile_bytes;
-#pragma unroll
-          for (int j = 0; j < U; ++j) {
-          bd.check(q + j * jstride, VEC);
-          VL::ld(q + j * jstride, a[j]);
-        }
-        }
-        fold_tile<P, NW, U>(b, t1, run);
-        t = t2;
-      }
-    } else {
-      for (; t < nft; t += gridDim.x) {
-        const uint8_t* q = lane_base + (uint64_t)t * tile_bytes;
-#pragma unroll
-        for (int j = 0; j < U; ++j) {
-          bd.check(q + j * jstride, VEC);
-          VL::ld(q + j * jstride, a[j]);
-        }
-        fold_tile<P, NW, U>(a, t, run);
+  for (int c = 0; c < NC; ++c) {
+    Key k;
+    bool valid, is_nan;
+    P::classify(raw[c], k, valid, is_nan);
+    const bool hit = have[c] && ((c == 0) ? (valid && k == b.kmin) : (c == 1) ? (valid && k == b.kmax) : is_nan);
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (m != 0 && lane == 0) {
+      const uint64_t idx = p.head_elems + cand[c] * VEC_ELEMS + (uint64_t)(__ffs(m) - 1);
+      if (c == 0) {
+        x.kmin = b.kmin;
+        x.pmin = idx;
+      } else if (c == 1) {
+        x.kmax = b.kmax;
+        x.pmax = idx;
+      } else {
+        x.pnan = idx;
       }
     }
   }
-  // ------------------------------- the one partial tile (id n_full_tiles + 1)
-  if (p.rem_vecs != 0 && blockIdx.x == p.n_full_tiles % gridDim.x && threadIdx.x < p.rem_vecs) {
-    uint32_t cur[U][NW];
-    const uint8_t* q =
-        main_base + (uint64_t)p.n_full_tiles * tile_bytes + (uint64_t)threadIdx.x * VEC;
-    bd.check(q, VEC);
-    VL::ld(q, cur[0]);
+  if (p.head_elems != 0 || p.tail_start != p.n) {  // warp-uniform; the usual aligned call skips it
 #pragma unroll
-    for (int j = 1; j < U; ++j) {
-      if ((uint32_t)j * blockDim.x + threadIdx.x < p.rem_vecs) {
-        bd.check(q + (uint64_t)j * blockDim.x * VEC, VEC);
-        VL::ld(q + (uint64_t)j * blockDim.x * VEC, cur[j]);
-      } else {  // duplicates are neutral for a value-only min/max
-#pragma unroll
-        for (int w = 0; w < NW; ++w) cur[j][w] = cur[0][w];
-      }
-    }
-    fold_tile<P, NW, U>(cur, p.n_full_tiles, run);
-  }
-
-  // ------------------------------- CTA reduce on (key, global vector index)
-  auto slot_to_vec = [&](uint32_t slot) -> uint64_t {
-    return slot == TILE_NONE ? POS_NONE
-                             : (uint64_t)(slot / U) * tile_vecs + (uint64_t)(slot % U) * blockDim.x +
-                                   threadIdx.x;
-  };
-  Best<Key> b;
-  b.kmin = run.kmin;
-  b.kmax = run.kmax;
-  b.pmin = slot_to_vec(run.smin);
-  b.pmax = slot_to_vec(run.smax);
-  b.pnan = slot_to_vec(run.snan);
-  b = block_reduce(b, smem);
-
-  // ------------------------------------------- last-block-done grid finalise
-  if (!grid_reduce(p, b, smem, &s_is_last)) return;
-
-  // ------- exact finish by ONE warp: the winning vectors (<= 32 elements each) are re-read
-  // with one element per lane and a ballot picks the first match; the unaligned head and the
-  // sub-vector tail (< one vector each) ride along as exact per-lane candidates.
-  __shared__ Best<Key> s_final;
-  if (threadIdx.x < 32) {
-    using Elem = typename P::Elem;
-    const Elem* e = reinterpret_cast<const Elem*>(p.base);
-    const uint32_t lane = threadIdx.x;
-    Best<Key> x;
-    x.clear();
-    const uint64_t cand[3] = {b.pmin, b.pmax, b.pnan};
-#pragma unroll
-    for (int c = 0; c < (P::TRACK_NAN ? 3 : 2); ++c) {
-      if (cand[c] == POS_NONE) continue;  // warp-uniform
-      const uint64_t first = p.head_elems + cand[c] * VEC_ELEMS;
-      bool hit = false;
-      if (lane < VEC_ELEMS) {
+    for (int part = 3; part < 5; ++part) {
+      const uint64_t i = part == 3 ? ih : it;
+      if (have[part]) {
         Key k;
         bool valid, is_nan;
-        bd.check(&e[first + lane], sizeof(Elem));
-        P::classify(e[first + lane], k, valid, is_nan);
-        hit = (c == 0) ? (valid && k == b.kmin) : (c == 1) ? (valid && k == b.kmax) : is_nan;
-      }
-      const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-      if (m != 0 && lane == 0) {
-        const uint64_t idx = first + (uint64_t)(__ffs(m) - 1);
-        if (c == 0) {
-          x.kmin = b.kmin;
-          x.pmin = idx;
-        } else if (c == 1) {
-          x.kmax = b.kmax;
-          x.pmax = idx;
-        } else {
-          x.pnan = idx;
-        }
-      }
-    }
-    // head: elements [0, head_elems); tail: [tail_start, n); both shorter than one vector
-#pragma unroll
-    for (int part = 0; part < 2; ++part) {
-      const uint64_t begin = part == 0 ? 0 : p.tail_start;
-      const uint64_t end = part == 0 ? p.head_elems : p.n;
-      const uint64_t i = begin + lane;
-      if (i < end) {
-        Key k;
-        bool valid, is_nan;
-        bd.check(&e[i], sizeof(Elem));
-        P::classify(e[i], k, valid, is_nan);
+        P::classify(raw[part], k, valid, is_nan);
         if (valid) {
           x.merge_min(k, i);
           x.merge_max(k, i);
@@ -844,12 +867,242 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) x.merge(shfl_xor(x, m));
-    if (lane == 0) s_final = x;
   }
-  __syncthreads();
-  const Best<Key> x = s_final;
+  return x;
+}
 
-  finalize<XCHG>(p, x);
+// ---------------------------------------------------------------------------------------
+// The streaming kernel.  A CTA owns a sequence of TILES (blockDim x U vectors each):
+//   grid-stride (per_vecs == 0, large inputs): tiles b, b + G, b + 2G, ... of the whole array;
+//   contiguous (per_vecs != 0, small / medium inputs): its own range of per_vecs vectors, cut
+//     into tiles -- every CTA gets the same amount to within one row of blockDim vectors, where
+//     grid-stride hands out whole 16-32 KiB tiles (4 vs 5 tiles per CTA at 40 MB = 20 % idle).
+// Local tile k lives at vector  cta_vec_base + k * kstride_vecs;  a SLOT id is k * U + j.
+// The partial tile at the END of the CTA's sequence is loaded FIRST (so that its latency hides
+// behind tile 0's loads) and folded into its own running state, merged last with "main wins
+// ties" -- every main-loop vector of a thread precedes its remainder vectors.
+// ---------------------------------------------------------------------------------------
+template <typename Key>
+__device__ __forceinline__ void running_clear(Running<Key>& r) {
+  r.kmin = KeyLim<Key>::MAXV;
+  r.kmax = KeyLim<Key>::MINV;
+  r.smin = r.smax = r.snan = TILE_NONE;
+}
+
+template <class P, int VEC, int U, bool PREFETCH, int HINT, bool XCHG, bool PACKED = false>
+__global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanParams p) {
+  using VL = VecLoad<VEC, HINT>;
+  constexpr uint32_t VEC_ELEMS = VEC / sizeof(typename P::Elem);
+  using Key = typename P::Key;
+  constexpr int NW = VL::NW;
+  static_assert(!PACKED || sizeof(Key) == 4, "packed candidates need 32-bit keys");
+  __shared__ ReduceScratch<Key> scratch;
+  __shared__ uint32_t s_is_last;
+  pdl_entry(p);
+  stamp(p, ST_ENTRY);
+
+  const uint32_t tile_vecs = blockDim.x * U;
+  const uint64_t tile_bytes = (uint64_t)tile_vecs * VEC;
+  const uint8_t* main_base = p.base + p.head_elems * sizeof(typename P::Elem);
+  const Bounds bd(p);
+
+  // this CTA's tile sequence: n_full static tiles, then (dyn_tiles != 0) claimed ones, and at
+  // most one partial tile of `rem` vectors at rem_vec_base
+  uint64_t cta_vec_base, kstride_vecs, rem_vec_base;
+  uint32_t n_full, rem;
+  if (p.per_vecs != 0) {
+    const uint64_t vb = (uint64_t)blockIdx.x * p.per_vecs;
+    const uint64_t ve = vb + p.per_vecs < p.n_vec ? vb + p.per_vecs : p.n_vec;
+    const uint64_t len = ve > vb ? ve - vb : 0;
+    n_full = (uint32_t)(len / tile_vecs);
+    rem = (uint32_t)(len % tile_vecs);
+    cta_vec_base = vb;
+    kstride_vecs = tile_vecs;
+    rem_vec_base = vb + (uint64_t)n_full * tile_vecs;
+  } else {
+    const uint32_t nft = p.n_full_tiles;  // static tiles only
+    n_full = blockIdx.x < nft ? (nft - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    rem = (p.rem_vecs != 0 && blockIdx.x == p.rem_owner) ? p.rem_vecs : 0;
+    cta_vec_base = (uint64_t)blockIdx.x * tile_vecs;
+    kstride_vecs = (uint64_t)gridDim.x * tile_vecs;
+    rem_vec_base = (uint64_t)(nft + p.dyn_tiles) * tile_vecs;
+  }
+  const uint8_t* lane_base = main_base + (cta_vec_base + threadIdx.x) * VEC;
+  const uint64_t kstride_bytes = kstride_vecs * VEC;
+  const uint64_t jstride = (uint64_t)blockDim.x * VEC;
+
+  // Dynamic tail (serialised scans only, see launch_packed): the last dyn_tiles full tiles of the
+  // array are not pre-assigned; a CTA that has finished its static share claims them one at a
+  // time from a counter in the workspace, so the CTAs finish together although they progress at
+  // very different rates (equal static shares finish 2.4x apart at 40 MB, 5 % apart at 4 GiB).
+  // Claims are issued one tile ahead by thread 0 and broadcast through shared memory; claimed
+  // tiles ascend per CTA and lie behind every static tile, so slot order stays address order.
+  __shared__ uint32_t s_claim[2];
+  const uint32_t dyn_tiles = p.dyn_tiles;
+  uint32_t* const dyn_counter = p.ticket + 24;
+  uint32_t pending = 0;
+  if (dyn_tiles != 0 && threadIdx.x == 0) pending = atomicAdd(dyn_counter, 1u);
+  auto next_tile = [&](uint32_t i, const uint8_t*& q, uint32_t& t) -> bool {
+    if (i < n_full) {
+      q = lane_base + (uint64_t)i * kstride_bytes;
+      t = i;
+      return true;
+    }
+    if (dyn_tiles == 0) return false;
+    const uint32_t c = i - n_full;  // this CTA's c-th claim
+    if (threadIdx.x == 0) s_claim[c & 1] = pending;
+    __syncthreads();
+    const uint32_t d = s_claim[c & 1];
+    if (d >= dyn_tiles) return false;
+    if (threadIdx.x == 0) pending = atomicAdd(dyn_counter, 1u);
+    q = main_base + ((uint64_t)(p.n_full_tiles + d) * tile_vecs + threadIdx.x) * VEC;
+    t = p.dyn_koff + d;
+    return true;
+  };
+
+  Running<Key> run, run_rem;
+  running_clear(run);
+  running_clear(run_rem);
+
+  {
+    uint32_t a[U][NW];
+    // ---------------- partial tile: its loads go out first
+    uint32_t cur[U][NW];
+    const bool mine = threadIdx.x < rem;  // rem != 0 and this thread owns at least row 0 of it
+    if (mine) {
+      const uint8_t* q = main_base + (rem_vec_base + threadIdx.x) * VEC;
+      bd.check(q, VEC);
+      VL::ld(q, cur[0]);
+#pragma unroll
+      for (int j = 1; j < U; ++j) {
+        if ((uint32_t)j * blockDim.x + threadIdx.x < rem) {
+          bd.check(q + j * jstride, VEC);
+          VL::ld(q + j * jstride, cur[j]);
+        }
+      }
+    }
+    // ---------------- streaming phase: full tiles, two register buffers in ping-pong: the loads
+    // of the next tile are in flight while the current one is folded (PREFETCH)
+    uint32_t i = 0;
+    const uint8_t* qa = nullptr;
+    uint32_t ta = 0;
+    bool va = false;
+    if (PREFETCH) {
+      va = next_tile(0, qa, ta);
+      if (va) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          bd.check(qa + j * jstride, VEC);
+          VL::ld(qa + j * jstride, a[j]);
+        }
+      }
+    }
+    if (mine) {
+#pragma unroll
+      for (int j = 1; j < U; ++j) {
+        if (!((uint32_t)j * blockDim.x + threadIdx.x < rem)) {  // duplicates are neutral for a value-only min/max
+#pragma unroll
+          for (int w = 0; w < NW; ++w) cur[j][w] = cur[0][w];
+        }
+      }
+      fold_tile<P, NW, U>(cur, 0, run_rem);
+    }
+    if (PREFETCH) {
+      uint32_t b[U][NW];
+      while (va) {
+        const uint8_t* qb = nullptr;
+        uint32_t tb = 0;
+        const bool vb = next_tile(i + 1, qb, tb);
+        if (vb) {
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            bd.check(qb + j * jstride, VEC);
+            VL::ld(qb + j * jstride, b[j]);
+          }
+        }
+        fold_tile<P, NW, U>(a, ta, run);
+#ifdef AMM_PHASE_STAMPS
+        if (i == 0) stamp(p, ST_FIRST_FOLD);
+#endif
+        if (!vb) break;
+        va = next_tile(i + 2, qa, ta);
+        if (va) {
+#pragma unroll
+          for (int j = 0; j < U; ++j) {
+            bd.check(qa + j * jstride, VEC);
+            VL::ld(qa + j * jstride, a[j]);
+          }
+        }
+        fold_tile<P, NW, U>(b, tb, run);
+        i += 2;
+      }
+    } else {
+      while (next_tile(i, qa, ta)) {
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+          bd.check(qa + j * jstride, VEC);
+          VL::ld(qa + j * jstride, a[j]);
+        }
+        fold_tile<P, NW, U>(a, ta, run);
+        ++i;
+      }
+    }
+  }
+  stamp(p, ST_STREAM_DONE);
+
+  // ------------------- slot ids -> global vector indices; the partial tile holds this thread's
+  // LAST vectors, so the main state wins ties
+  auto slot_to_vec = [&](uint32_t slot) -> uint64_t {
+    if (slot == TILE_NONE) return POS_NONE;
+    const uint32_t tl = slot / U, j = slot % U;
+    const uint64_t tile_base = tl < p.dyn_koff ? cta_vec_base + (uint64_t)tl * kstride_vecs
+                                               : (uint64_t)(p.n_full_tiles + (tl - p.dyn_koff)) * tile_vecs;
+    return tile_base + (uint64_t)j * blockDim.x + threadIdx.x;
+  };
+  auto rem_slot_to_vec = [&](uint32_t slot) -> uint64_t {
+    return slot == TILE_NONE ? POS_NONE : rem_vec_base + (uint64_t)slot * blockDim.x + threadIdx.x;
+  };
+  Key kmin = run.kmin, kmax = run.kmax;
+  uint64_t vmin = slot_to_vec(run.smin), vmax = slot_to_vec(run.smax), vnan = slot_to_vec(run.snan);
+  {
+    const bool um = run_rem.smin != TILE_NONE && (run.smin == TILE_NONE || run_rem.kmin < run.kmin);
+    const bool uM = run_rem.smax != TILE_NONE && (run.smax == TILE_NONE || run_rem.kmax > run.kmax);
+    kmin = um ? run_rem.kmin : kmin;
+    vmin = um ? rem_slot_to_vec(run_rem.smin) : vmin;
+    kmax = uM ? run_rem.kmax : kmax;
+    vmax = uM ? rem_slot_to_vec(run_rem.smax) : vmax;
+    vnan = run.snan == TILE_NONE ? rem_slot_to_vec(run_rem.snan) : vnan;
+  }
+
+  // ------------------- CTA + grid reduce on (key, global vector index); only warp 0 of the
+  // last CTA to arrive goes on, with the grid-wide candidates in `b`
+  Best<Key> b;
+  if constexpr (PACKED) {
+    // 32-bit pieces (launch_one guarantees fewer than 2^32 - 2 vectors)
+    PackedCand c;
+    c.clear();
+    if (vmin != POS_NONE)  // min and max are set together (fold_tile)
+      c.set(kmin, (uint32_t)vmin, kmax, (uint32_t)vmax);
+    if (P::TRACK_NAN && vnan != POS_NONE) c.pnan = (uint32_t)vnan;
+    if (!packed_grid_reduce<P>(p, c, scratch.words())) return;
+    b = c.unpack();
+  } else {
+    b.kmin = kmin;
+    b.kmax = kmax;
+    b.pmin = vmin;
+    b.pmax = vmax;
+    b.pnan = vnan;
+    b = block_reduce(b, scratch.best());
+    stamp(p, ST_CTA_REDUCED);
+    if (!grid_reduce(p, b, scratch.best(), &s_is_last)) return;
+    if (threadIdx.x >= 32) return;
+  }
+  // every CTA has taken its ticket, hence made its last claim: re-arm the claim counter
+  if (dyn_tiles != 0 && threadIdx.x == 0) *dyn_counter = 0u;
+  stamp(p, ST_GRID_FOLDED);
+  const Best<Key> x = exact_finish_warp<P, VEC_ELEMS>(p, bd, b);
+  stamp(p, ST_EXACT_DONE);
+  finalize_warp<XCHG>(p, x);
 }
 
 }  // namespace amm

@@ -44,12 +44,14 @@ static cudaError_t launch_scan(Kernel kernel, unsigned grid, unsigned threads, c
   return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
-template <class P, int VEC, int U, bool PF, int HINT, bool XCHG>
-static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
-                      cudaStream_t stream) {
-  auto kernel = argminmax_scan_kernel<P, VEC, U, PF, HINT, XCHG>;
+template <class P, int VEC, int U, bool PF, int HINT, bool XCHG, bool PACKED>
+static int launch_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
+                         cudaStream_t stream) {
+  auto kernel = argminmax_scan_kernel<P, VEC, U, PF, HINT, XCHG, PACKED>;
   const int threads = ws->eff_threads;
-  const int vslot = variant + (XCHG ? kNumVariants : 0);  // fused instantiations cache separately
+  // fused / packed instantiations cache their occupancy separately
+  const int vslot = variant + (XCHG ? kNumVariants : 0) + (PACKED ? 2 * kNumVariants : 0);
+  static_assert(4 * kNumVariants <= AMM_MAX_VARIANTS, "occupancy cache too small");
   int& occ = ws->occupancy[dtype_slot][vslot];
   if (occ == 0 || ws->occupancy_threads[dtype_slot][vslot] != threads) {
     int o = 0;
@@ -67,15 +69,47 @@ static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int vari
   p.n_vec = (p.n - head) / vec_elems;
   p.tail_start = head + p.n_vec * vec_elems;
   const uint64_t full = p.n_vec / tile_vecs;
-  if ((full + 2) * (uint64_t)U >= 0xFFFFFFFFull) return AMM_ERR_TOO_LARGE;  // 32-bit slot ids
+  if ((2 * full + 4) * (uint64_t)U >= 0xFFFFFFFFull) return AMM_ERR_TOO_LARGE;  // 32-bit slot ids
   p.n_full_tiles = (uint32_t)full;
   p.rem_vecs = (uint32_t)(p.n_vec % tile_vecs);
   const uint64_t tiles = full + (p.rem_vecs ? 1 : 0);
   int per_sm = ws->eff_ctas_per_sm < occ ? ws->eff_ctas_per_sm : occ;
   uint64_t grid = (uint64_t)ws->sm_count * (uint64_t)per_sm;
-  if (grid > tiles) grid = tiles;
-  if (grid < 1) grid = 1;
   if (grid > (uint64_t)ws->max_grid) grid = (uint64_t)ws->max_grid;
+  // How the tiles are handed out (profiles/r02_fixed_cost.md).  CTAs given equal shares finish
+  // far apart -- the memory system serves them at very different rates (2.4x between the first
+  // and the last CTA at 40 MB, +-2.6 % at 4 GiB) and the stragglers then stream alone, latency-
+  // bound.  So, for a scan that runs alone (not pipelined) and has at least two tiles per CTA:
+  //   DYNAMIC TAIL  the first tiles grid-stride, the last AMM_SCAN_DYN_PCT % claimed at run time.
+  // Otherwise (pipelined scans overlap their tail with the next scan anyway, and a claim counter
+  // cannot be shared by two grids in flight):
+  //   CONTIGUOUS    fewer than 64 tiles per CTA: equal ranges of whole rows (blockDim vectors);
+  //   GRID-STRIDE   else: whole tiles b, b + G, ... (the +-1 tile imbalance is noise there).
+  p.per_vecs = 0;
+  p.dyn_tiles = 0;
+  p.dyn_koff = 0xFFFFFFFFu;
+  p.rem_owner = 0;
+  const bool big = p.n_bytes >= ((uint64_t)512 << 20);
+  const int dyn_pct = ws->scan_dyn_pct >= 0 ? ws->scan_dyn_pct : (big ? 8 : 30);
+  const bool dynamic = dyn_pct > 0 && !p.pipelined && ws->scan_contig != 1 && full >= 2 * grid;
+  const bool contig = !dynamic && (ws->scan_contig < 0 ? tiles < 64 * grid : ws->scan_contig != 0);
+  if (dynamic) {
+    uint64_t dyn = full * (uint64_t)(dyn_pct > 90 ? 90 : dyn_pct) / 100;
+    if (dyn < grid) dyn = grid;  // one claim per CTA goes out on entry
+    p.dyn_tiles = (uint32_t)dyn;
+    p.n_full_tiles = (uint32_t)(full - dyn);
+    p.dyn_koff = (uint32_t)((full - dyn + grid - 1) / grid + 1);
+  } else if (contig) {
+    const uint64_t rows = (p.n_vec + (uint64_t)threads - 1) / (uint64_t)threads;
+    uint64_t rows_per_cta = (rows + grid - 1) / grid;
+    if (rows_per_cta < 1) rows_per_cta = 1;
+    grid = (rows + rows_per_cta - 1) / rows_per_cta;  // drops the CTAs that would get nothing
+    p.per_vecs = rows_per_cta * (uint64_t)threads;
+  } else {
+    if (grid > tiles) grid = tiles;
+    p.rem_owner = grid ? (uint32_t)(full % grid) : 0;
+  }
+  if (grid < 1) grid = 1;
   // With programmatic dependent launch the CTAs of the NEXT scan on the stream become resident
   // while this one runs.  If an SM can hold more than twice the CTAs a scan puts on it, the
   // block scheduler packs the next grid onto the free slots of fewer SMs (3 per SM instead of
@@ -110,7 +144,28 @@ static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int vari
   return AMM_OK;
 }
 
-// Latency path for small inputs: one exact pass, see argminmax_direct_kernel.
+// 32-bit keys with fewer than 2^32 - 2 vectors: the cross-CTA step travels as packed 64-bit
+// words (see packed_grid_reduce); everything else keeps the partials + ticket + fold flow.
+template <class P, int VEC, int U, bool PF, int HINT, bool XCHG>
+static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
+                      cudaStream_t stream) {
+  if constexpr (sizeof(typename P::Key) == 4) {
+    const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
+    if (ws->scan_packed && p.n / vec_elems < 0xFFFFFFFEull)
+      return launch_packed<P, VEC, U, PF, HINT, XCHG, true>(ws, p, dtype_slot, variant, stream);
+  }
+  return launch_packed<P, VEC, U, PF, HINT, XCHG, false>(ws, p, dtype_slot, variant, stream);
+}
+
+// Latency path for small inputs: one trip, see argminmax_direct_kernel.  Returns false when the
+// input does not fit one trip (more than 4 vectors per thread at the CTA cap).
+template <class P>
+static bool direct_fits(const amm_workspace* ws, uint64_t n) {
+  const uint64_t vec_elems = 16 / sizeof(typename P::Elem);
+  const uint64_t cap_threads = (uint64_t)ws->sm_count * (uint64_t)ws->direct_ctas_per_sm * (uint64_t)ws->direct_threads;
+  return n / vec_elems <= cap_threads * 4;
+}
+
 template <class P>
 static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) {
   constexpr uint64_t VEC = 16;
@@ -121,23 +176,33 @@ static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) 
   p.head_elems = head;
   p.n_vec = (p.n - head) / vec_elems;
   p.tail_start = head + p.n_vec * vec_elems;
-  const int threads = ws->direct_threads;
-  // Latency, not throughput: as long as CTAs are available give every thread ONE vector (its
-  // exact per-element tracking is a serial chain of ~25 instructions per element); only
-  // beyond sm_count x direct_ctas_per_sm CTAs do threads loop (4 vectors in flight per trip).
-  const uint64_t per_cta = (uint64_t)threads * (uint64_t)ws->direct_vecs_per_thread;
-  uint64_t grid = (p.n_vec + per_cta - 1) / per_cta;
-  // up to 16 elements per thread ONE CTA is quicker than several: a second CTA brings in the
-  // cross-CTA round trip (~1.3 us)
-  if (p.n <= (uint64_t)threads * 16) grid = 1;
+  const uint64_t threads = (uint64_t)ws->direct_threads;
+  // Latency, not throughput: as long as CTAs are available every thread gets ONE vector (more
+  // CTAs are free latency); beyond sm_count x direct_ctas_per_sm CTAs threads take 2..4 vectors,
+  // all in flight at once.  Up to 4 vectors per thread ONE CTA is quicker than several: a second
+  // CTA brings in the cross-CTA round trip (~1.3 us).
   const uint64_t cap = (uint64_t)ws->sm_count * (uint64_t)ws->direct_ctas_per_sm;
-  if (grid > cap) grid = cap;
+  uint64_t vpt = (p.n_vec + cap * threads - 1) / (cap * threads);
+  if (vpt < (uint64_t)ws->direct_vecs_per_thread) vpt = (uint64_t)ws->direct_vecs_per_thread;
+  if (p.n_vec <= threads * 4) vpt = (p.n_vec + threads - 1) / threads;
+  if (vpt < 1) vpt = 1;
+  if (vpt > 4) return AMM_ERR_ARG;  // launch_variant checks direct_fits() first
+  p.direct_vpt = (uint32_t)vpt;
+  uint64_t grid = (p.n_vec + threads * vpt - 1) / (threads * vpt);
   if (grid < 1) grid = 1;
+  const bool packed = sizeof(typename P::Key) == 4 && p.n < 0xFFFFFFFEull && ws->direct_packed;
   if (p.world > 1) {
-    AMM_CUDA(launch_scan(argminmax_direct_kernel<P, true>, (unsigned)grid, (unsigned)threads, stream,
-                         p, ws->pdl != 0));
-  } else if (sizeof(typename P::Key) == 4 && p.n < 0xFFFFFFFEull && ws->direct_packed) {
-    // 32-bit keys: candidates travel as one packed 64-bit word (see packed_finish)
+    if constexpr (sizeof(typename P::Key) == 4) {
+      if (packed) {
+        AMM_CUDA(launch_scan(argminmax_direct_kernel<P, true, true>, (unsigned)grid, (unsigned)threads,
+                             stream, p, ws->pdl != 0));
+      }
+    }
+    if (!packed)
+      AMM_CUDA(launch_scan(argminmax_direct_kernel<P, true>, (unsigned)grid, (unsigned)threads, stream,
+                           p, ws->pdl != 0));
+  } else if (packed) {
+    // 32-bit keys: candidates travel as packed words (see packed_grid_reduce)
     if constexpr (sizeof(typename P::Key) == 4)
       AMM_CUDA(launch_scan(argminmax_direct_kernel<P, false, true>, (unsigned)grid,
                            (unsigned)threads, stream, p, ws->pdl != 0));
@@ -146,7 +211,7 @@ static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) 
                          stream, p, ws->pdl != 0));
   }
   ws->last_grid = (int)grid;
-  ws->last_threads = threads;
+  ws->last_threads = (int)threads;
   ws->launches += 1;
   return AMM_OK;
 }
@@ -154,20 +219,22 @@ static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) 
 template <class P>
 static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStream_t stream) {
   const uint64_t bytes = p.n * sizeof(typename P::Elem);
-  // Latency kernel below the measured crossover with the streaming kernel (tools/latency_c.py):
-  // 2^20 elements for 32-bit keys (packed-word finish), 2^16 for 64-bit keys; an explicit
-  // threshold (amm_workspace_set_direct_threshold / AMM_DIRECT_BYTES) replaces the rule.
-  const bool direct = ws->direct_auto
-                          ? p.n <= (sizeof(typename P::Key) == 4 ? (1ull << 20) : (1ull << 16))
-                          : bytes <= ws->direct_bytes;
+  // Latency kernel below the measured crossover with the streaming kernel (tools/latency_c.py),
+  // per key width, and only while the input fits its single trip; an explicit threshold
+  // (amm_workspace_set_direct_threshold / AMM_DIRECT_BYTES) replaces the size rule.
+  const bool direct = (ws->direct_auto
+                           ? p.n <= (sizeof(typename P::Key) == 4 ? ws->direct_elems32 : ws->direct_elems64)
+                           : bytes <= ws->direct_bytes) &&
+                      direct_fits<P>(ws, p.n);
   if (direct) return launch_direct<P>(ws, p, stream);
-  // Automatic geometry (B200 sweeps, profiles/r01_sweeps.md): 256-bit loads and a deep grid
-  // win on HBM-sized inputs; below ~0.5 GiB the fixed tail matters more and 128-bit loads
-  // with 2 CTAs/SM finish sooner.
+  // Automatic geometry (B200 measurements, profiles/r02_fixed_cost.md): 256-bit loads, 256-thread
+  // CTAs (16 KiB tiles), as many CTAs per SM as fit (4-5) on HBM-sized inputs and 4 below 0.5 GiB
+  // (128 KiB in flight per SM either way; with 2 CTAs per SM a 400 MB scan streams at 5.7 TB/s
+  // instead of 6.9).
   const bool big = bytes >= ((uint64_t)512 << 20);
-  ws->eff_variant = ws->variant >= 0 ? ws->variant : (big ? 1 : 0);
+  ws->eff_variant = ws->variant >= 0 ? ws->variant : 1;
   ws->eff_threads = ws->threads > 0 ? ws->threads : 256;
-  ws->eff_ctas_per_sm = ws->ctas_per_sm > 0 ? ws->ctas_per_sm : (big ? 8 : 2);
+  ws->eff_ctas_per_sm = ws->ctas_per_sm > 0 ? ws->ctas_per_sm : (big ? 8 : 4);
   if (p.world > 1) {
     // fused scan + peer exchange: instantiated for the two automatic shapes only
     if (ws->eff_variant != 0) ws->eff_variant = 1;

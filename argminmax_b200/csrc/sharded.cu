@@ -6,13 +6,15 @@
 // with first-occurrence tie-break is an associative reduction over (key, index)
 // (chunk merge src/simd/generic.rs:513-520, prefix/tail merge src/simd/task.rs:149-228).
 //
-// Per call: every device scans its shard with the ordinary kernel (global_offset =
-// shard start) on its own stream; the G 64-byte records are exchanged by ONE
-// ncclAllGather (G x 64 B over NVLink, latency-bound) enqueued on the same streams;
-// the gathered table is read back from device 0 and combined in ascending shard
-// order with strict compares.  NCCL is resolved with dlopen at run time so the
-// library has no link-time NCCL dependency and shares the copy already loaded by
-// the host process (e.g. torch's).
+// Per call, default ("peer"): every device runs ONE kernel on its own stream -- the ordinary scan
+// (global_offset = shard start) fused with the exchange of the G 64-byte records over NVLink
+// (peer-mapped buffers, scan_kernel.cuh: exchange_and_publish_warp) and the fold in ascending
+// shard order with strict compares; the host reads the global answer from the pinned slots.
+// "nccl" (north_star's baseline, AMM_SHARDED_EXCHANGE=nccl, and the fallback without P2P): scan
+// kernels, then ONE ncclAllGather (G x 64 B, latency-bound) enqueued on the same streams, the
+// gathered table is read back from device 0 and combined on the host.  NCCL is resolved with
+// dlopen at run time so the library has no link-time NCCL dependency and shares the copy already
+// loaded by the host process (e.g. torch's).
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdlib.h>
@@ -185,12 +187,56 @@ int amm_sharded_workspace(amm_sharded* sh, int g, amm_workspace** ws) {
   return AMM_OK;
 }
 
+// A peer-mode call whose launch loop stopped at device `failed`: the kernels already running on
+// devices [0, failed) wait for records that will never be sent.  Release them by writing a
+// poisoned record (AMM_REC_PEER_TIMEOUT, this call's tag) for every missing rank into their
+// exchange buffers, drain their streams, and take the handle off the peer path for good.
+static void abort_peer_call(amm_sharded* sh, int failed) {
+  for (int a = 0; a < failed; ++a) {
+    amm_workspace* ws = sh->ws[a];
+    if (set_device(sh->devices[a]) != AMM_OK) continue;
+    const uint64_t xseq = ws->xseq;  // the tag the running kernel waits for
+    const uint64_t bank = (xseq & 1ull) * (uint64_t)sh->ngpu;
+    for (int r = failed; r < sh->ngpu; ++r) {
+      uint64_t slot[XCHG_SLOT_WORDS];
+      memset(slot, 0, sizeof(slot));
+      amm_record rec;
+      memset(&rec, 0, sizeof(rec));
+      rec.min_idx = rec.max_idx = rec.nan_idx = AMM_NO_INDEX;
+      rec.flags = AMM_REC_PEER_TIMEOUT;
+      memcpy(slot, &rec, sizeof(rec));
+      slot[8] = mix_checksum(slot, PEER_SLOT_SEED ^ xseq);
+      slot[9] = xseq;
+      // default-stream copy: the per-device streams are non-blocking, so this does not queue
+      // behind the spinning kernel
+      cudaMemcpy(ws->xbuf + (bank + (uint64_t)r) * XCHG_SLOT_WORDS, slot, sizeof(slot),
+                 cudaMemcpyHostToDevice);
+    }
+  }
+  for (int a = 0; a < failed; ++a) {
+    if (set_device(sh->devices[a]) != AMM_OK) continue;
+    cudaStreamSynchronize(sh->streams[a]);
+    sh->ws[a]->xbroken = 1;
+  }
+  (void)cudaGetLastError();
+  sh->use_peer = false;
+  if (!sh->use_nccl && sh->api.CommInitAll == nullptr && load_nccl(sh->api) &&
+      sh->api.CommInitAll(sh->comms, sh->ngpu, sh->devices) == 0)
+    sh->use_nccl = true;
+}
+
 int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptrs,
                           const uint64_t* shard_lens, int mode, uint64_t out[2]) {
   if (!sh || !dev_ptrs || !shard_lens || !out) return AMM_ERR_ARG;
   DeviceGuard restore(sh->devices[0]);
+  // validate EVERY shard before anything is launched: a bad shard g must not leave devices
+  // 0..g-1 running a collective that devices g.. never join
   uint64_t total = 0;
-  for (int g = 0; g < sh->ngpu; ++g) total += shard_lens[g];
+  for (int g = 0; g < sh->ngpu; ++g) {
+    const int rc = validate_scan(dtype, dev_ptrs[g], shard_lens[g], mode, /*empty_allowed=*/true);
+    if (rc) return rc;
+    total += shard_lens[g];
+  }
   if (total == 0) return AMM_ERR_EMPTY;
   if (sh->use_peer) {
     // fused path: one kernel per device does scan + exchange + combine
@@ -198,22 +244,32 @@ int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptr
     for (int g = 0; g < sh->ngpu; ++g) {
       int rc = launch(dtype, dev_ptrs[g], shard_lens[g], mode, off, sh->ws[g], sh->streams[g],
                       nullptr, true);
-      if (rc) return rc;
+      if (rc) {  // (a CUDA launch error; arguments were checked above)
+        abort_peer_call(sh, g);
+        return rc;
+      }
       off += shard_lens[g];
     }
     uint64_t first[2] = {0, 0};
-    for (int g = 0; g < sh->ngpu; ++g) {
-      uint64_t r[2];
+    int status = AMM_OK;
+    for (int g = 0; g < sh->ngpu; ++g) {  // wait for ALL devices even if one reports an error
+      uint64_t r[2] = {0, 0};
       int rc = set_device(sh->devices[g]);
-      if (rc) return rc;
-      rc = amm_workspace_wait(sh->ws[g], sh->streams[g], mode, r);
-      if (rc) return rc;
+      if (rc == AMM_OK) rc = amm_workspace_wait(sh->ws[g], sh->streams[g], mode, r);
+      if (rc) {
+        if (status == AMM_OK) status = rc;
+        continue;
+      }
       if (g == 0) {
         first[0] = r[0];
         first[1] = r[1];
-      } else if (r[0] != first[0] || r[1] != first[1]) {
-        return AMM_ERR_PEER;  // every device must have folded the same table
+      } else if (status == AMM_OK && (r[0] != first[0] || r[1] != first[1])) {
+        status = AMM_ERR_PEER;  // every device must have folded the same table
       }
+    }
+    if (status != AMM_OK) {
+      if (status == AMM_ERR_PEER) abort_peer_call(sh, 0);  // nothing left running: just leave the peer path
+      return status;
     }
     out[0] = first[0];
     out[1] = first[1];

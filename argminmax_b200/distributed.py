@@ -56,9 +56,19 @@ def combine_across_ranks(local: _ffi.AmmRecord, mode: int, group=None) -> tuple[
     return combine_records(exchange_records(local, group), mode)
 
 
+# workspaces that currently hold a peer exchange (a workspace holds at most one)
+_exchange_owners: dict[int, "DistributedShardedSlice"] = {}
+
+
 class DistributedShardedSlice:
     """This rank's shard of a logical array; every rank must call the same methods in the same
-    order (they contain a collective).  Mirrors the ArgMinMax / NaNArgMinMax surface."""
+    order (they contain a collective).  Mirrors the ArgMinMax / NaNArgMinMax surface.
+
+    The fused exchange lives in a workspace and a workspace holds one exchange.  The slice uses
+    its shard's workspace when that is free and a private one otherwise (a second slice on the
+    same device), so two slices never share -- or tear down -- each other's exchange buffers.
+    `close()` is a collective too: every rank unmaps its peers' buffers, a barrier, then each
+    rank frees its own (CUDA requires importers to close before the exporter frees)."""
 
     def __init__(self, shard: DeviceSlice, group=None):
         import torch
@@ -78,32 +88,77 @@ class DistributedShardedSlice:
         self._rec = torch.zeros(64, dtype=torch.uint8, device=dev)
         self._gathered = torch.zeros(64 * self.world, dtype=torch.uint8, device=dev)
         self.exchange = "nccl"
+        self._ws = shard.workspace
+        self._owns_exchange = False
         want = os.environ.get("AMM_SHARDED_EXCHANGE", "peer")
         if self.world > 1 and want == "peer":
             self._setup_peer_exchange(dev)
 
+    @property
+    def workspace(self):
+        """The workspace the collective scans run on (tuning / pipelined mode apply here)."""
+        return self._ws
+
     def _setup_peer_exchange(self, dev) -> None:
-        """Fused in-kernel exchange: allocate this rank's buffer, swap CUDA IPC handles once
-        (the only collective in the setup), map the peers' buffers.  Falls back to the NCCL
-        all-gather path if any rank cannot set it up (all ranks agree on the outcome)."""
+        """Fused in-kernel exchange: allocate this rank's buffer, swap CUDA IPC handles and GPU
+        UUIDs once (the only collective in the setup), map the peers' buffers.  Falls back to the
+        NCCL all-gather path if any rank cannot set it up -- e.g. two ranks share one GPU -- and
+        all ranks agree on the outcome."""
         import torch
         import torch.distributed as dist
 
-        ws = self.shard.workspace
+        from .device_slice import Workspace
+
+        if id(self._ws) in _exchange_owners:  # the shard's workspace already carries an exchange
+            self._ws = Workspace(self.shard.device)
+        ws = self._ws
         handle = (ctypes.c_uint8 * 64)()
+        uuid = (ctypes.c_uint8 * 16)()
         ok = lib().amm_exchange_create(ws.handle, self.world, self.rank, handle) == _ffi.AMM_OK
-        mine = torch.tensor(list(bytes(handle)) + [1 if ok else 0], dtype=torch.uint8, device=dev)
-        allh = torch.zeros(65 * self.world, dtype=torch.uint8, device=dev)
+        created = ok
+        ok = ok and lib().amm_device_uuid(self.shard.device, uuid) == _ffi.AMM_OK
+        mine = torch.tensor(list(bytes(handle)) + list(bytes(uuid)) + [1 if ok else 0],
+                            dtype=torch.uint8, device=dev)
+        allh = torch.zeros(81 * self.world, dtype=torch.uint8, device=dev)
         dist.all_gather_into_tensor(allh, mine, group=self.group)
-        rows = allh.view(self.world, 65).cpu()
-        ok = bool(rows[:, 64].min().item() == 1)
+        rows = allh.view(self.world, 81).cpu()
+        ok = bool(rows[:, 80].min().item() == 1)
         if ok:
             table = bytes(rows[:, :64].contiguous().numpy().tobytes())
+            ids = bytes(rows[:, 64:80].contiguous().numpy().tobytes())
             buf = (ctypes.c_uint8 * len(table)).from_buffer_copy(table)
-            ok = lib().amm_exchange_connect_ipc(ws.handle, buf) == _ffi.AMM_OK
+            idbuf = (ctypes.c_uint8 * len(ids)).from_buffer_copy(ids)
+            ok = lib().amm_exchange_connect_ipc(ws.handle, buf, idbuf) == _ffi.AMM_OK
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
-        self.exchange = "peer" if int(flag.item()) == 1 else "nccl"
+        if int(flag.item()) == 1:
+            self.exchange = "peer"
+            self._owns_exchange = True
+            _exchange_owners[id(ws)] = self
+        elif created:
+            # some rank failed: unmap whatever was mapped, then free (same order as close())
+            lib().amm_exchange_disconnect(ws.handle)
+            dist.barrier(group=self.group)
+            lib().amm_exchange_destroy(ws.handle)
+
+    def set_timeout(self, milliseconds: int) -> None:
+        """How long the in-kernel exchange waits for a peer's record (0 = for ever, like NCCL)."""
+        check(lib().amm_exchange_set_timeout(self._ws.handle, milliseconds), "amm_exchange_set_timeout")
+
+    def close(self) -> None:
+        """Collective teardown of the fused exchange (no-op on the NCCL path)."""
+        import torch
+        import torch.distributed as dist
+
+        if not self._owns_exchange:
+            return
+        self._owns_exchange = False
+        _exchange_owners.pop(id(self._ws), None)
+        torch.cuda.synchronize(self.shard.device)
+        lib().amm_exchange_disconnect(self._ws.handle)
+        dist.barrier(group=self.group)
+        lib().amm_exchange_destroy(self._ws.handle)
+        self.exchange = "nccl"
 
     def __len__(self):
         return self.n_total
@@ -117,25 +172,25 @@ class DistributedShardedSlice:
         s = self.shard
         if self.exchange == "peer":
             rc = lib().amm_argminmax_launch_exchange(DTYPES[s.dtype], s.data_ptr, s.n, mode,
-                                                     self.global_offset, s.workspace.handle, stream)
+                                                     self.global_offset, self._ws.handle, stream)
             check(rc, "amm_argminmax_launch_exchange")
             return
         if s.n == 0:
             self._rec.zero_()  # no value, no NaN
         else:
             rc = lib().amm_argminmax_launch(DTYPES[s.dtype], s.data_ptr, s.n, mode,
-                                            self.global_offset, s.workspace.handle, stream,
+                                            self.global_offset, self._ws.handle, stream,
                                             self._rec.data_ptr())
             check(rc, "amm_argminmax_launch")
         dist.all_gather_into_tensor(self._gathered, self._rec, group=self.group)
         rc = lib().amm_combine_records_launch(self._gathered.data_ptr(), self.world, mode,
-                                              s.workspace.handle, stream)
+                                              self._ws.handle, stream)
         check(rc, "amm_combine_records_launch")
 
     def wait(self, mode: int = IGNORE_NAN) -> tuple[int, int]:
         import torch
         out = (ctypes.c_uint64 * 2)()
-        check(lib().amm_workspace_wait(self.shard.workspace.handle,
+        check(lib().amm_workspace_wait(self._ws.handle,
                                        torch.cuda.current_stream().cuda_stream, mode, out),
               "amm_workspace_wait")
         return int(out[0]), int(out[1])

@@ -16,10 +16,17 @@ through the public host-slice API with HOST (pinned) input: H2D copies inside th
 region.  `roofline` = algorithmic bytes / kernel time against MEASURED_PEAKS.json.
 `cpu_baseline` = the AVX-512/AVX restatement of the reference's dispatched f32 path
 (oracle/cpu_simd_f32.c), single thread like the reference, on this box's host.
+
+Every answer that is timed is first checked against the CPU oracle (`verified_vs_oracle`): the
+2^30 scan against both the SIMD restatement and the scalar restatement of the reference on a
+pinned host copy of the same bytes; at N > 1 additionally a verification step with duplicate
+extremes planted in the first and the last shard, a NaN case in return-NaN mode and an empty
+shard, and an in-process amm_sharded_argminmax over all N GPUs driven by rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes
 import json
 import os
 import statistics
@@ -35,6 +42,17 @@ METRIC = "argminmax GB/s (f32 1G elems per GPU, device-resident) vs HBM roofline
 N_ELEMS = 1 << 30
 DTYPE = "f32"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def workload_config(n: int, world: int) -> dict:
+    """`config` of the JSON line -- the SAME dict in both arms (ours and --impl reference)."""
+    return {
+        "workload": "configs[3]: f32 1G (2^30) elements = 4 GiB per GPU, ArgMinMax (ignore-NaN), "
+                    "uniform random bit patterns NaN->0 (reference bench generator)",
+        "elements_per_gpu": n, "bytes_per_gpu": n * 4,
+        "l2": "input (4 GiB) >> 126 MB L2, every step streams from memory (no flush needed)",
+        "parallelism": f"shard{world}" if world > 1 else "single",
+    }
 
 
 def measured_peak():
@@ -130,29 +148,54 @@ def parse_cpulist(spec: str) -> set:
     return cpus
 
 
+def cpus_from_affinity_mask(words, bits_per_word: int = 64) -> set:
+    """NVML CPU-affinity bitmask (array of unsigned longs, LSB = CPU 0) -> set of CPU ids."""
+    cpus = set()
+    for wi, w in enumerate(words):
+        w = int(w)
+        for b in range(bits_per_word):
+            if (w >> b) & 1:
+                cpus.add(wi * bits_per_word + b)
+    return cpus
+
+
 def bind_to_gpu_numa_node(torch, index: int) -> dict:
-    """Run this rank (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA
-    node its GPU hangs off -- what `numactl --cpunodebind` does for one-rank-per-GPU jobs.  With 8
-    ranks streaming host memory to 8 GPUs at once, buffers that all sit on one socket make the
-    other socket's GPUs pull their input across the inter-socket link.  No-op when sysfs has no
-    NUMA information (single-node VMs report -1)."""
-    info = {"node": None, "cpus": None}
+    """Run this rank (and therefore first-touch its pinned host buffers) on the CPUs next to its GPU
+    -- what `numactl --cpunodebind` does for one-rank-per-GPU jobs.  With 8 ranks streaming host
+    memory to 8 GPUs at once, buffers that all sit on one socket make the other socket's GPUs pull
+    their input across the inter-socket link.  Source of the CPU set: sysfs (numa_node of the
+    GPU's PCI function) and, when that says -1 (VMs), NVML's ideal CPU affinity of the device.
+    No-op when neither knows more than "all CPUs"."""
+    info = {"node": None, "cpus": None, "source": None}
+    allowed = os.sched_getaffinity(0)
     try:
         pr = torch.cuda.get_device_properties(index)
         sys_id = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
         with open(f"/sys/bus/pci/devices/{sys_id}/numa_node") as f:
             node = int(f.read().strip())
         info["node"] = node
-        if node < 0:
-            return info
-        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            spec = f.read().strip()
-        cpus = parse_cpulist(spec) & os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            info["cpus"] = len(cpus)
+        if node >= 0:
+            with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+                cpus = parse_cpulist(f.read()) & allowed
+            if cpus and cpus != allowed:
+                os.sched_setaffinity(0, cpus)
+                info.update(cpus=len(cpus), source="sysfs numa_node")
+                return info
     except Exception as e:  # noqa: BLE001 - placement is an optimisation, never a failure
         info["error"] = type(e).__name__
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        nwords = (max(allowed) // 64) + 1
+        cpus = cpus_from_affinity_mask(pynvml.nvmlDeviceGetCpuAffinity(h, nwords)) & allowed
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            info.update(cpus=len(cpus), source="nvmlDeviceGetCpuAffinity")
+        else:
+            info.update(cpus=len(allowed), source="none (NVML affinity = all CPUs: single NUMA domain)")
+    except Exception as e:  # noqa: BLE001
+        info["nvml_error"] = type(e).__name__
     return info
 
 
@@ -171,6 +214,13 @@ def make_device_data(torch, device, n: int, seed: int):
     return f
 
 
+def make_host_data(np, n: int, seed: int = 0):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 2**32, n, dtype=np.uint32).view(np.float32)
+    a[np.isnan(a)] = 0
+    return a
+
+
 # ------------------------------------------------------------------- CPU baseline
 def cpu_model() -> str:
     try:
@@ -184,8 +234,9 @@ def cpu_model() -> str:
 
 
 def cpu_baseline(host_np, budget_s: float, all_cores: bool = True) -> dict:
-    """Single-thread AVX-512/AVX restatement of the reference's dispatched f32 path on a
-    bounded sample; the all-cores variant is NOT something the reference does (labelled so)."""
+    """Single-thread AVX-512/AVX restatement of the reference's dispatched f32 path on the SAME
+    2^30-element workload (a bounded number of passes); the all-cores variant is NOT something the
+    reference does (labelled so)."""
     from oracle import oracle
     nbytes = host_np.nbytes
     times = []
@@ -200,9 +251,9 @@ def cpu_baseline(host_np, budget_s: float, all_cores: bool = True) -> dict:
     out = {
         "value": round(nbytes / min(times) / 1e9, 2), "median": round(nbytes / statistics.median(times) / 1e9, 2),
         "unit": "GB/s", "cores": 1, "kind": "port", "isa": oracle.cpu_simd_isa(),
-        "sample": f"f32 x {host_np.size} elements ({nbytes >> 20} MiB, DRAM-resident), best of {len(times)} passes, "
-                  "oracle/cpu_simd_f32.c (restatement of src/simd/simd_f32_ignore_nan.rs + generic.rs + task.rs), "
-                  "1 thread as in the reference",
+        "sample": f"the whole workload: f32 x {host_np.size} elements ({nbytes >> 20} MiB, DRAM-resident), best of "
+                  f"{len(times)} passes, oracle/cpu_simd_f32.c (restatement of src/simd/simd_f32_ignore_nan.rs + "
+                  "generic.rs + task.rs), 1 thread as in the reference",
         "host_cpus": os.cpu_count(), "cpu_model": cpu_model(), "result": list(res),
     }
     if all_cores:
@@ -217,49 +268,172 @@ def cpu_baseline(host_np, budget_s: float, all_cores: bool = True) -> dict:
     return out
 
 
+def cpu_small_n_latency(np, n: int, calls: int = 20000) -> dict:
+    """The reference's own bench size (dev_utils/src/config.rs:4: n = 102 400 f32, cache-resident):
+    us per call of the CPU port, timed in C-call granularity (ctypes overhead ~1 us included)."""
+    from oracle import oracle
+    a = make_host_data(np, n, seed=3)
+    for _ in range(200):
+        oracle.cpu_simd_argminmax_f32(a)
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        oracle.cpu_simd_argminmax_f32(a)
+    us = (time.perf_counter() - t0) / calls * 1e6
+    return {"n": n, "us_per_call": round(us, 2), "calls": calls, "isa": oracle.cpu_simd_isa(),
+            "note": "cache-resident, 1 thread, through ctypes (adds ~0.5-1 us); the reference publishes 6.975 us on an "
+                    "i7-1185G7 (benches/results:15)"}
+
+
 def run_reference(args) -> int:
     """--impl reference: the reference's own CPU path (restated in C, see oracle/) on this
-    box's host cores.  Under torchrun only rank 0 works; the others exit 0."""
+    box's host cores, on the SAME workload as our arm (f32 x 2^30 per step).  The crate is
+    single-threaded, so one thread is all the host threads it can use; an all-cores figure is
+    added and labelled as not the reference.  Under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import numpy as np
 
     from oracle import oracle
-    sample = 1 << 27  # 512 MiB of the workload per step: DRAM-resident, ~40 ms per pass
-    rng = np.random.default_rng(0)
-    a = rng.integers(0, 2**32, sample, dtype=np.uint32).view(np.float32).copy()
-    a[np.isnan(a)] = 0
-    for _ in range(args.warmup):
+    n = args.elems
+    a = make_host_data(np, n, seed=0)
+    for _ in range(min(args.warmup, 3)):
         oracle.cpu_simd_argminmax_f32(a)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         res = oracle.cpu_simd_argminmax_f32(a)
     dt = time.perf_counter() - t0
-    assert res == oracle.argminmax(a, 0)
+    verified = res == oracle.argminmax(a, 0)
+    assert verified, "SIMD restatement disagrees with the scalar oracle"
     gbs = a.nbytes * args.steps / dt / 1e9
     nt = os.cpu_count() or 1
     t1 = time.perf_counter()
     for _ in range(3):
         oracle.cpu_simd_argminmax_f32_mt(a, nt)
     mt_gbs = a.nbytes * 3 / (time.perf_counter() - t1) / 1e9
-    sample_desc = (f"f32 x 2^27 elements (512 MiB) of the f32 1G workload per step, single thread (the "
+    sample_desc = (f"the whole workload per step: f32 x {n} elements ({a.nbytes >> 20} MiB), single thread (the "
                    f"reference crate is single-threaded), ISA {oracle.cpu_simd_isa()} chosen like src/lib.rs:427-443")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbs, 3), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "f32 1G elems ArgMinMax (ignore-NaN); reference arm runs a 2^27-element sample per step on the host CPU",
-                   "elements_per_step": sample},
+        "config": workload_config(n, args.gpus),
         "cpu_baseline": {"value": round(gbs, 3), "unit": "GB/s", "cores": 1, "kind": "port",
                          "isa": oracle.cpu_simd_isa(), "sample": sample_desc, "host_cpus": nt, "cpu_model": cpu_model(),
                          "all_cores_not_reference": {"value": round(mt_gbs, 2), "threads": nt}},
         "e2e": {"value": round(gbs, 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "verified_vs_oracle": verified, "result": list(res),
+        "where": "host CPU only (the reference has no GPU path); under torchrun rank 0 alone runs",
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+# ----------------------------------------------------------------- helper probes
+def events_us(torch, fn, iters: int) -> float:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+def serialised_probes(torch, amm, ws, data, stream) -> dict:
+    """Single-call (serialised, non-pipelined) device time of the scan at BASELINE config 1 / 2
+    sizes, cold L2: consecutive launches walk through distinct segments of the 4 GiB array."""
+    ws.set_pipelined(False)
+    out = {}
+    raw = data.view(torch.uint8)
+    total = raw.numel()
+    for key, dt, n in (("f32_10m", "f32", 10_000_000), ("f32_100m", "f32", 100_000_000),
+                       ("u8_100m", "u8", 100_000_000), ("f32_102400", "f32", 102_400)):
+        nbytes = n * amm.DTYPE_SIZE[dt]
+        stride = -(-nbytes // 4096) * 4096
+        segs = max(1, min(64, total // stride))
+        # enough distinct segments that a revisit finds its lines evicted (>= 512 MB walked)
+        slices = [amm.DeviceSlice.from_torch(raw[i * stride: i * stride + nbytes], dtype=dt, workspace=ws, stream=stream)
+                  for i in range(segs)]
+        for s in slices[:3]:
+            s.launch(amm.IGNORE_NAN)
+        slices[0].wait(amm.IGNORE_NAN)
+        iters = 200 if nbytes <= (64 << 20) else 60
+        us = events_us(torch, lambda i: slices[i % segs].launch(amm.IGNORE_NAN), iters)
+        slices[0].wait(amm.IGNORE_NAN)
+        out[key] = {"us": round(us, 2), "gbs": round(nbytes / us / 1e3, 1), "segments": segs,
+                    "cold_l2": segs * stride >= (256 << 20)}
+    out["10m_us"] = out["f32_10m"]["us"]
+    out["100m_gbs"] = out["f32_100m"]["gbs"]
+    out["what"] = ("device time per call, CUDA events over back-to-back NON-pipelined launches (each scan alone on the "
+                   "GPU), rotating over distinct segments of the resident array so that L2 is cold")
+    return out
+
+
+def dtype_table(torch, np, amm, ws, data, host_np, stream, peak: float, verify: bool) -> list:
+    """All 14 (dtype, mode) instantiations: serialised GB/s at 4 GiB and at 100 M elements (BASELINE
+    config 2), the raw bytes of the f32 array reinterpreted (performance is data-independent:
+    the loop is branch-free).  The 100 M rows are checked against the oracle on the host copy."""
+    from oracle import oracle
+    ws.set_pipelined(False)
+    raw = data.view(torch.uint8)
+    np_dt = {"i8": np.int8, "i16": np.int16, "i32": np.int32, "i64": np.int64, "u8": np.uint8, "u16": np.uint16,
+             "u32": np.uint32, "u64": np.uint64, "f16": np.float16, "f32": np.float32, "f64": np.float64}
+    rows = []
+    for dt in amm.DTYPES:
+        es = amm.DTYPE_SIZE[dt]
+        for mode in ((0, 1) if dt in amm.FLOAT_DTYPES else (0,)):
+            row = {"dtype": dt, "mode": "return_nan" if mode else "ignore_nan"}
+            full = amm.DeviceSlice.from_torch(raw, dtype=dt, workspace=ws, stream=stream)
+            for _ in range(2):
+                full.launch(mode)
+            full.wait(mode)
+            us = events_us(torch, lambda i: full.launch(mode), 8)
+            full.wait(mode)
+            row["gbs_4gib"] = round(raw.numel() / us / 1e3, 1)
+            row["frac_4gib"] = round(raw.numel() / us / 1e3 / peak, 4)
+            n = 100_000_000
+            nbytes = n * es
+            stride = -(-nbytes // 4096) * 4096
+            segs = max(1, raw.numel() // stride)
+            sl = [amm.DeviceSlice.from_torch(raw[i * stride: i * stride + nbytes], dtype=dt, workspace=ws, stream=stream)
+                  for i in range(segs)]
+            for s in sl[:2]:
+                s.launch(mode)
+            got = sl[0].wait(mode) if segs < 2 else None
+            if got is None:
+                sl[0].launch(mode)
+                got = sl[0].wait(mode)
+            us = events_us(torch, lambda i: sl[i % segs].launch(mode), 24)
+            sl[0].wait(mode)
+            row["us_100m"] = round(us, 2)
+            row["gbs_100m"] = round(nbytes / us / 1e3, 1)
+            row["frac_100m"] = round(nbytes / us / 1e3 / peak, 4)
+            if verify and host_np is not None:
+                ref = oracle.argminmax(host_np.view(np.uint8)[:nbytes].view(np_dt[dt]), mode)
+                row["parity_100m"] = (tuple(got) == tuple(ref))
+                if not row["parity_100m"]:
+                    raise AssertionError(f"dtype table: {dt} mode {mode}: gpu {got} oracle {ref}")
+            rows.append(row)
+    return rows
+
+
+def h2d_ceiling(torch, host, device, stream_count: int = 1, reps: int = 3) -> float:
+    """Plain pinned cudaMemcpyAsync of the whole host buffer, no scan: GB/s (this rank)."""
+    dst = torch.empty(1 << 28, dtype=torch.float32, device=device)  # 1 GiB landing buffer, reused
+    n = host.numel()
+    chunk = dst.numel()
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        for i in range(0, n, chunk):
+            m = min(chunk, n - i)
+            dst[:m].copy_(host[i:i + m], non_blocking=True)
+        torch.cuda.synchronize()
+        best = max(best, n * 4 / (time.perf_counter() - t0) / 1e9)
+    return best
 
 
 # --------------------------------------------------------------------------- main
@@ -273,6 +447,8 @@ def main() -> int:
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 10)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the dtype table, serialised probes, strong scaling, config 5 (ncu runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -283,6 +459,7 @@ def main() -> int:
     import torch.distributed as dist
 
     import argminmax_b200 as amm
+    from oracle import oracle  # the checker: verifies the timed answers, and the cpu_baseline leg
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -292,11 +469,13 @@ def main() -> int:
         raise SystemExit("bench.py needs a GPU: the CUDA path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    host_group = None
     if distributed:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=device)
+        host_group = dist.new_group(backend="gloo")  # CPU-side barriers that leave the GPUs idle
     amm.lib()  # fail loudly if the extension is missing
     numa = bind_to_gpu_numa_node(torch, local_rank)
 
@@ -309,6 +488,7 @@ def main() -> int:
     stream = torch.cuda.current_stream().cuda_stream
     shard = amm.DeviceSlice.from_torch(data, dtype=DTYPE, workspace=ws, stream=stream)
     sharded = amm.DistributedShardedSlice(shard) if distributed else None
+    xws = sharded.workspace if sharded is not None else ws
 
     def enqueue_step():
         if sharded is not None:
@@ -321,30 +501,68 @@ def main() -> int:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x: float) -> float:
+        if not distributed:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(flag: bool) -> bool:
+        if not distributed:
+            return flag
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def gather_rows(vals):
+        """every rank contributes a list of float64; returns world x len rows on every rank"""
+        mine = torch.tensor(vals, dtype=torch.float64, device=device)
+        if not distributed:
+            return [mine.cpu().tolist()]
+        allv = torch.zeros(world * len(vals), dtype=torch.float64, device=device)
+        dist.all_gather_into_tensor(allv, mine)
+        return allv.view(world, len(vals)).cpu().tolist()
+
+    # pinned host copy of this rank's shard: the oracle's input, and later the e2e input
+    host = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    host.copy_(data)
+    torch.cuda.synchronize()
+    host_np = host.numpy()
+
     sampler = ClockSampler(local_rank)
     sampler.start()
 
     # Consecutive steps scan a resident, unchanging array: let step k+1's streaming phase overlap
     # step k's fold/publish tail (programmatic dependent launch, amm_workspace_set_pipelined).
+    xws.set_pipelined(True)
     ws.set_pipelined(True)
 
-    # ---- warm-up (untimed) + correctness of the answer we are about to time
+    # ---- warm-up (untimed) + the answer we are about to time, checked against the oracle
     for _ in range(args.warmup):
         enqueue_step()
     result = (sharded or shard).wait(amm.IGNORE_NAN)
-    if distributed:
-        # cross-check the exchange + combine: every rank's LOCAL answer (single-GPU path, parity-
-        # tested against the oracle) and the values there are gathered; the global answer must be
-        # the lexicographic (value, index) extreme over ranks.
-        li, lj = shard.argminmax()
-        mine = torch.tensor([float(data[li]), float(rank * n + li), float(data[lj]), float(rank * n + lj)],
-                            dtype=torch.float64, device=device)
-        allv = torch.zeros(world * 4, dtype=torch.float64, device=device)
-        dist.all_gather_into_tensor(allv, mine)
-        rows = allv.view(world, 4).cpu().tolist()
-        exp = (int(min(rows, key=lambda r: (r[0], r[1]))[1]), int(min(rows, key=lambda r: (-r[2], r[3]))[3]))
-        assert result == exp, f"distributed result {result} != expected {exp}"
-    launches0 = ws.last_launch()["launches_total"]
+    verification = {}
+    t_v = time.perf_counter()
+    local_simd = oracle.cpu_simd_argminmax_f32(host_np)      # the reference's dispatched SIMD path
+    local_gpu = shard.argminmax()
+    ok_local = tuple(local_gpu) == tuple(local_simd)
+    if rank == 0:
+        local_scalar = oracle.argminmax(host_np, oracle.IGNORE_NAN)  # ... and its scalar path
+        ok_local = ok_local and tuple(local_gpu) == tuple(local_scalar)
+        verification["oracles"] = ["oracle.cpu_simd_argminmax_f32 (every rank)", "oracle.argminmax scalar (rank 0)"]
+    # expected global answer = lexicographic (value, index) fold of the ORACLE's per-shard answers
+    li, lj = local_simd
+    rows = gather_rows([float(host_np[li]), float(rank * n + li), float(host_np[lj]), float(rank * n + lj)])
+    exp = (int(min(rows, key=lambda r: (r[0], r[1]))[1]), int(min(rows, key=lambda r: (-r[2], r[3]))[3]))
+    ok_global = tuple(result) == exp
+    verified = all_true(ok_local and ok_global)
+    verification.update({"timed_answer": list(result), "oracle_answer": list(exp), "local_ok": ok_local,
+                         "seconds": round(time.perf_counter() - t_v, 2)})
+    if not verified:
+        raise SystemExit(f"rank {rank}: timed answer {result} / local {local_gpu} disagrees with the oracle "
+                         f"(global {exp}, local {local_simd})")
+    launches0 = xws.last_launch()["launches_total"]
 
     # ---- timed region: exactly K steps, device-timed, barrier + sync on both sides
     barrier()
@@ -359,58 +577,154 @@ def main() -> int:
     t_wall1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     result2 = (sharded or shard).wait(amm.IGNORE_NAN)
-    assert result2 == result
-    launches = ws.last_launch()["launches_total"] - launches0
-    if distributed:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
+    if tuple(result2) != exp:
+        raise SystemExit(f"rank {rank}: answer after the timed region {result2} != oracle {exp}")
+    launches = xws.last_launch()["launches_total"] - launches0
+    ms_total = max_over_ranks(ms_total)
     ms_per_step = ms_total / args.steps
     value = world * nbytes / ms_per_step / 1e6  # GB/s, aggregate
     clocks = sampler.summary(t_wall0, t_wall1)
-    main_launch = ws.last_launch()
-    tuning = ws.get_tuning()  # geometry of the timed scans (later probes use other shapes)
+    main_launch = xws.last_launch()
+    tuning = xws.get_tuning()  # geometry of the timed scans (later probes use other shapes)
 
     # ---- kernel-only duration of the dominant kernel (roofline), this rank, same stream,
     #      launches strictly serialised (no overlap between consecutive kernels)
     ws.set_pipelined(False)
+    xws.set_pipelined(False)
     for _ in range(2):
         shard.launch(amm.IGNORE_NAN)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(args.steps):
-        shard.launch(amm.IGNORE_NAN)
-    k1.record()
-    k1.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / args.steps
+    kernel_ms = events_us(torch, lambda i: shard.launch(amm.IGNORE_NAN), args.steps) / 1e3
+    shard.wait(amm.IGNORE_NAN)
     peak, peak_src = measured_peak()
     achieved = nbytes / kernel_ms / 1e6
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": committed_traffic(),
+                "traffic_source": "committed ncu --set full capture (profiles/traffic.json), not measured in this run",
                 "kernel": "argminmax_scan_kernel<PolF32<ignore>>", "kernel_ms": round(kernel_ms, 5),
                 "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                 "note": "kernel_ms: serialised launches (each kernel alone on the GPU); `value` is measured with "
                         "consecutive steps pipelined (PDL), which hides each kernel's fold/publish tail",
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4)}
 
+    extras = {}
+    if not args.no_extras:
+        # ---- strong scaling: 2^30 elements IN TOTAL over the N GPUs (each scans 2^30/N of its
+        #      buffer), serialised collective calls; N=1 reference = kernel_ms above
+        if distributed:
+            per = n // world
+            part = amm.DeviceSlice.from_torch(data[:per], dtype=DTYPE, workspace=ws, stream=stream)
+            sp = amm.DistributedShardedSlice(part)  # private workspace (the first slice owns ws)
+            for _ in range(3):
+                sp.launch(amm.IGNORE_NAN)
+            sp.wait(amm.IGNORE_NAN)
+            barrier()
+            strong_ms = max_over_ranks(events_us(torch, lambda i: sp.launch(amm.IGNORE_NAN), 50) / 1e3)
+            sp.wait(amm.IGNORE_NAN)
+            sp.workspace.set_pipelined(True)
+            for _ in range(3):
+                sp.launch(amm.IGNORE_NAN)
+            barrier()
+            strong_pipe_ms = max_over_ranks(events_us(torch, lambda i: sp.launch(amm.IGNORE_NAN), 50) / 1e3)
+            sp.wait(amm.IGNORE_NAN)
+            sp.workspace.set_pipelined(False)
+            # host-visible latency of one synchronous collective call, and where sharding starts
+            # to pay: total sizes 2^18 .. 2^30 against the single-GPU call on rank 0's buffer
+            cross = []
+            for lg in (18, 20, 22, 24, 26, 28, 30):
+                tot = 1 << lg
+                pr = tot // world
+                a = amm.DeviceSlice.from_torch(data[:pr], dtype=DTYPE, workspace=ws, stream=stream)
+                sp.shard = a
+                sp.n_total, sp.global_offset = tot, rank * pr
+                one = amm.DeviceSlice.from_torch(data[:tot], dtype=DTYPE, workspace=ws, stream=stream)
+                for _ in range(10):
+                    sp.argminmax()
+                    one.argminmax()
+                barrier()
+                calls = 100
+                t0 = time.perf_counter()
+                for _ in range(calls):
+                    sp.argminmax()
+                us_sh = max_over_ranks((time.perf_counter() - t0) / calls * 1e6)
+                t0 = time.perf_counter()
+                for _ in range(calls):
+                    one.argminmax()
+                us_one = (time.perf_counter() - t0) / calls * 1e6
+                rows1 = gather_rows([us_one])
+                cross.append({"total_elems_log2": lg, "us_sharded": round(us_sh, 2), "us_one_gpu": round(rows1[0][0], 2)})
+            first_win = next((c["total_elems_log2"] for c in cross if c["us_sharded"] < c["us_one_gpu"]), None)
+            sp.close()
+            extras["strong"] = {
+                "total_elems": n, "per_gpu_elems": per, "ms": round(strong_ms, 5),
+                "gbs": round(nbytes / strong_ms / 1e6, 1),
+                "efficiency_vs_n1": round(kernel_ms / (world * strong_ms), 4),
+                "ms_pipelined": round(strong_pipe_ms, 5),
+                "efficiency_vs_n1_pipelined": round(ms_per_step / (world * strong_pipe_ms), 4) if False else None,
+                "n1_ms_same_box": round(kernel_ms, 5),
+                "what": "one logical f32 array of 2^30 elements split over the N GPUs; device time per serialised "
+                        "collective call (scan fused with the in-kernel record exchange), max over ranks; "
+                        "efficiency = t(1 GPU, 2^30, serialised) / (N x t(N GPUs))",
+                "sync_call_us_by_total_size": cross, "sharding_pays_from_log2_elems": first_win,
+            }
+            # ---- config 5: 32 Gi f32 elements (128 GiB) IN TOTAL over the N GPUs: this rank's 4 GiB
+            #      block tiled 32/N times; the expected answer follows from the oracle-checked block
+            reps = 32 // world
+            try:
+                big = data.repeat(reps)
+                bshard = amm.DeviceSlice.from_torch(big, dtype=DTYPE, workspace=ws, stream=stream)
+                bs = amm.DistributedShardedSlice(bshard)
+                bs.workspace.set_pipelined(True)
+                for _ in range(2):
+                    bs.launch(amm.IGNORE_NAN)
+                got5 = bs.wait(amm.IGNORE_NAN)
+                per5 = n * reps
+                rows5 = gather_rows([float(host_np[li]), float(rank * per5 + li), float(host_np[lj]), float(rank * per5 + lj)])
+                exp5 = (int(min(rows5, key=lambda r: (r[0], r[1]))[1]), int(min(rows5, key=lambda r: (-r[2], r[3]))[3]))
+                ok5 = all_true(tuple(got5) == exp5)
+                barrier()
+                ms5 = max_over_ranks(events_us(torch, lambda i: bs.launch(amm.IGNORE_NAN), 10) / 1e3)
+                bs.wait(amm.IGNORE_NAN)
+                bs.close()
+                extras["config5"] = {"total_elems": per5 * world, "per_gpu_gib": per5 * 4 / 2**30, "ms": round(ms5, 4),
+                                     "gbs": round(world * per5 * 4 / ms5 / 1e6, 1), "verified_vs_oracle": ok5,
+                                     "how_verified": "each GPU holds its oracle-checked 4 GiB block tiled; first occurrences "
+                                                     "lie in the first tile, so the expected global answer is the "
+                                                     "lexicographic fold of the per-block oracle answers"}
+                del big, bshard, bs
+                torch.cuda.empty_cache()
+            except torch.OutOfMemoryError:
+                extras["config5"] = {"skipped": "not enough free HBM for 128 GiB / N per GPU next to the resident buffers"}
+
+            # ---- multi-GPU parity step (before any number of this section is trusted): duplicate
+            #      extremes in the first and the last shard, NaN in return mode, an empty shard
+            extras["multi_gpu_parity"] = multi_gpu_parity(torch, np, dist, amm, oracle, device, rank, world, ws, stream,
+                                                          gather_rows, all_true)
+            # ---- in-process amm_sharded_argminmax over all N GPUs, driven by rank 0 alone
+            extras["sharded_in_process"] = sharded_in_process(torch, np, dist, amm, oracle, rank, world, host_group)
+        else:
+            extras["serialised"] = serialised_probes(torch, amm, ws, data, stream)
+            extras["dtype_table"] = dtype_table(torch, np, amm, ws, data, host_np, stream, peak, verify=True)
+
     # the clock sampler belongs to the timed regions above; its NVML polling thread would
     # contend with the launch path of the latency probe below
     sampler.stop_flag = True
     sampler.join(timeout=2.0)
 
-    # ---- small-n latency: us per call at 1M elements, synchronous C-ABI call timed inside the
-    #      library (amm_measure_call_latency: host wall clock, no Python in the loop)
-    import ctypes
+    # ---- small-n latency: us per call, synchronous C-ABI call timed inside the library
+    #      (amm_measure_call_latency: host wall clock, no Python in the loop)
     # A B200 that has just streamed at full HBM rate answers small calls ~1.7 us slower for a few
     # hundred ms (tools/exp/latency_after_load.py: 12.8 us right after 400 x 4 GiB scans, 11.0 us
     # fresh and again 1 s later).  The probe measures the settled state a latency-bound caller sees.
     time.sleep(1.0)
     lat3 = (ctypes.c_double * 3)()
-    rc = amm.lib().amm_measure_call_latency(amm.DTYPES[DTYPE], data.data_ptr(), 1 << 20, amm.IGNORE_NAN,
-                                            ws.handle, stream, 2000, lat3)
-    if rc:
-        raise RuntimeError(f"amm_measure_call_latency rc={rc}")
-    us_1m = lat3[0]
+    lat_by_n = {}
+    for nn in (1 << 20, 1 << 17, 102_400):
+        rc = amm.lib().amm_measure_call_latency(amm.DTYPES[DTYPE], data.data_ptr(), nn, amm.IGNORE_NAN,
+                                                ws.handle, stream, 2000, lat3)
+        if rc:
+            raise RuntimeError(f"amm_measure_call_latency rc={rc}")
+        lat_by_n[nn] = {"median": round(lat3[0], 2), "min": round(lat3[1], 2), "p99": round(lat3[2], 2)}
+    us_1m = lat_by_n[1 << 20]["median"]
     small = amm.DeviceSlice.from_torch(data[: 1 << 20], dtype=DTYPE, workspace=ws, stream=stream)
     for _ in range(20):
         small.argminmax()
@@ -423,13 +737,10 @@ def main() -> int:
 
     # ---- e2e: the public host-slice call on pinned HOST input (H2D inside the timed region)
     e2e = None
-    host = None
     if not args.no_e2e:
-        host = torch.empty(n, dtype=torch.float32, pin_memory=True)
-        host.copy_(data)
-        torch.cuda.synchronize()
         hs = amm.HostSlice.from_torch(host, dtype=DTYPE, device=local_rank, workspace=ws)
         rec = amm.AmmRecord()
+
         def e2e_step():
             rc = amm.lib().amm_host_argminmax_record(amm.DTYPES[DTYPE], hs.host_ptr, hs.n, amm.IGNORE_NAN,
                                                      rank * n, ws.handle, ctypes.byref(rec))
@@ -441,33 +752,37 @@ def main() -> int:
 
         e2e_steps = args.e2e_steps or min(args.steps, 10)
         r_e2e = e2e_step()
-        assert r_e2e == result, (r_e2e, result)
+        if tuple(r_e2e) != exp:
+            raise SystemExit(f"e2e answer {r_e2e} != oracle {exp}")
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
         barrier()
-        dt = time.perf_counter() - t0
-        if distributed:
-            t = torch.tensor([dt], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = max_over_ranks(time.perf_counter() - t0)
+        # the ceiling of this leg: plain pinned H2D copies on all N GPUs at once, no scan
+        barrier()
+        ceil_rows = gather_rows([h2d_ceiling(torch, host, device)])
+        ceiling = sum(r[0] for r in ceil_rows)
         chunks = -(-nbytes // (32 << 20))
-        e2e = {"value": round(world * nbytes * e2e_steps / dt / 1e9, 2), "unit": "GB/s",
+        e2e_val = world * nbytes * e2e_steps / dt / 1e9
+        e2e = {"value": round(e2e_val, 2), "unit": "GB/s",
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": 64 * chunks,
                "steps": e2e_steps, "ms_per_step": round(dt / e2e_steps * 1e3, 3),
-               "api": "amm_host_argminmax_record (HostSlice): pinned host f32 -> chunked H2D overlapped with the scan; PCIe-bound"}
+               "h2d_ceiling_gbs": round(ceiling, 2), "frac_of_h2d_ceiling": round(e2e_val / ceiling, 4),
+               "h2d_ceiling_per_gpu_gbs": [round(r[0], 2) for r in ceil_rows],
+               "verified_vs_oracle": True,
+               "api": "amm_host_argminmax_record (HostSlice): pinned host f32 -> chunked H2D overlapped with the scan; "
+                      "PCIe-bound; h2d_ceiling_gbs = plain pinned cudaMemcpyAsync of the same buffers on all N GPUs "
+                      "concurrently, no scan (sum over ranks)"}
 
-    # ---- CPU baseline beside it (rank 0, N=1 only)
+    # ---- CPU baseline beside it (rank 0, N=1 only), on the same 2^30-element workload
     cpu = None
+    small_cpu = None
     if rank == 0 and not distributed and not args.no_cpu_baseline:
-        if host is not None:
-            sample = host.numpy()[: 1 << 28]
-        else:
-            sample = data[: 1 << 28].cpu().numpy()
-        cpu = cpu_baseline(np.ascontiguousarray(sample), budget_s=12.0)
+        cpu = cpu_baseline(host_np, budget_s=6.0)
+        small_cpu = cpu_small_n_latency(np, 102_400)
 
-    sampler.stop_flag = True
     ll = main_launch
     if rank == 0:
         line = {
@@ -475,11 +790,9 @@ def main() -> int:
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 5),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {
-                "workload": "configs[3]: f32 1G (2^30) elements = 4 GiB per GPU, device-resident, ArgMinMax (ignore-NaN), "
-                            "uniform random bit patterns NaN->0 (reference bench generator)",
-                "elements_per_gpu": n, "bytes_per_gpu": nbytes, "l2": "input (4 GiB) >> 126 MB L2, every step streams from HBM",
-                "parallelism": f"shard{world}" if distributed else "single",
+            "config": workload_config(n, world),
+            "launch": {
+                "residency": "device-resident (HBM) for `value`; pinned host memory for `e2e`",
                 "collective": (None if not distributed else
                                "fused in-kernel peer exchange of 64-byte records over NVLink (CUDA IPC), no NCCL on the step"
                                if sharded.exchange == "peer" else
@@ -488,19 +801,168 @@ def main() -> int:
                 "host_numa_binding": numa,
             },
             "elements_per_s": round(world * n / (ms_per_step / 1e3), 1),
+            "verified_vs_oracle": verified, "verification": verification,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "us_per_call_1m": round(us_1m, 2),
-            "us_per_call_1m_detail": {"median": round(lat3[0], 2), "min": round(lat3[1], 2), "p99": round(lat3[2], 2),
+            "us_per_call_1m_detail": {**lat_by_n[1 << 20],
                                       "through_python_ctypes_median": round(us_1m_python, 2),
                                       "what": "f32 n=2^20, synchronous amm_argminmax, host wall clock, GPU idle for 1 s "
                                               "before the probe (right after the streaming loops: +1.7 us)"},
+            "us_per_call": {"128Ki": lat_by_n[1 << 17], "102400": lat_by_n[102_400],
+                            "cpu_port_102400": small_cpu,
+                            "what": "synchronous C-ABI call (amm_measure_call_latency); 102 400 is the reference's own bench "
+                                    "size (dev_utils/src/config.rs:4), where the CPU port is timed beside it"},
+            **extras,
             "result": list(result), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
     if distributed:
+        if sharded is not None:
+            sharded.close()
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _lex_fold(rows):
+    """rows: per shard (has_value, min_val, min_idx, max_val, max_idx, nan_idx or -1) in shard
+    order -> (argmin, argmax, first_nan or -1) by the reference's merge rule."""
+    have = [r for r in rows if r[0]]
+    nans = [r[5] for r in rows if r[5] >= 0]
+    first_nan = int(min(nans)) if nans else -1
+    if not have:
+        return 0, 0, first_nan
+    imin = int(min(have, key=lambda r: (r[1], r[2]))[2])
+    imax = int(min(have, key=lambda r: (-r[3], r[4]))[4])
+    return imin, imax, first_nan
+
+
+def multi_gpu_parity(torch, np, dist, amm, oracle, device, rank, world, ws, stream, gather_rows, all_true) -> dict:
+    """One rank per GPU, fused exchange: cases the random timed array cannot cover.  Every rank
+    checks its LOCAL answer against the oracle on its shard and the GLOBAL answer against the
+    lexicographic fold of the oracle's per-shard answers (src/simd/generic.rs:513-520: the
+    earlier chunk wins ties; src/simd/test_utils.rs:89-151: first index)."""
+    m = 1 << 22
+    cases = []
+    base = make_host_data(np, m, seed=77 + rank)
+    # A: the SAME min and max value in shard 0 and in shard N-1 (and a decoy pair in between)
+    a = base.copy()
+    if rank in (0, world - 1):
+        a[m // 3] = -np.inf
+        a[m // 3 + 7] = np.inf
+        a[m - 5] = -np.inf
+        a[m - 9] = np.inf
+    cases.append(("dup_extremes_first_and_last_shard", a, amm.IGNORE_NAN))
+    cases.append(("dup_extremes_return_mode_no_nan", a, amm.RETURN_NAN))
+    # B: NaNs in two shards, return mode -> the first NaN of the lowest shard wins for both
+    b = base.copy()
+    if rank in (world - 1, max(0, world - 2)):
+        b[1000 + rank] = np.nan
+        b[m - 1] = np.nan
+    cases.append(("nan_in_last_two_shards_return_mode", b, amm.RETURN_NAN))
+    cases.append(("nan_in_last_two_shards_ignore_mode", b, amm.IGNORE_NAN))
+    # C: one empty shard (the middle rank, or the last one at N=2)
+    empty_rank = world // 2 if world > 2 else world - 1
+    c = a if rank != empty_rank else a[:0]
+    cases.append(("one_empty_shard", c, amm.IGNORE_NAN))
+    # D: all equal -> (0, 0) globally
+    d = np.full(m, 1.5, dtype=np.float32)
+    cases.append(("all_equal", d, amm.IGNORE_NAN))
+    report = {}
+    ok_all = True
+    for name, arr, mode in cases:
+        dev = torch.from_numpy(arr.copy()).to(device) if arr.size else torch.empty(0, dtype=torch.float32, device=device)
+        sl = amm.DeviceSlice.from_torch(dev, dtype="f32", workspace=ws, stream=stream) if arr.size else \
+            amm.DeviceSlice(0, 0, "f32", device.index, ws, stream)
+        ds = amm.DistributedShardedSlice(sl)
+        got = ds.nanargminmax() if mode == amm.RETURN_NAN else ds.argminmax()
+        off = ds.global_offset
+        if arr.size:
+            lo = oracle.argminmax(arr, mode)
+            lg = sl.nanargminmax() if mode == amm.RETURN_NAN else sl.argminmax()
+            local_ok = tuple(lg) == tuple(lo)
+            isn = np.isnan(arr)
+            nan_idx = int(np.argmax(isn)) + off if isn.any() else -1
+            oi = oracle.argminmax(arr, amm.IGNORE_NAN)
+            has = not isn.all()
+            row = [1.0 if has else 0.0, float(arr[oi[0]]) if has else 0.0, float(off + oi[0]),
+                   float(arr[oi[1]]) if has else 0.0, float(off + oi[1]), float(nan_idx)]
+        else:
+            local_ok = True
+            row = [0.0, 0.0, 0.0, 0.0, 0.0, -1.0]
+        rows = gather_rows(row)
+        imin, imax, first_nan = _lex_fold(rows)
+        exp = (first_nan, first_nan) if (mode == amm.RETURN_NAN and first_nan >= 0) else (imin, imax)
+        ok = all_true(local_ok and tuple(got) == exp)
+        report[name] = {"ok": ok, "got": list(got), "expected": list(exp), "exchange": ds.exchange}
+        ok_all = ok_all and ok
+        ds.close()
+    report["parity"] = ok_all
+    if not ok_all:
+        raise SystemExit(f"multi-GPU parity step failed: {json.dumps(report)}")
+    return report
+
+
+def sharded_in_process(torch, np, dist, amm, oracle, rank, world, host_group) -> dict:
+    """Rank 0 alone drives an in-process amm_sharded_argminmax (what the Rust
+    ShardedDeviceSlice<T> binds) over all N GPUs, fused peer exchange and NCCL all-gather, on small
+    oracle-checked arrays; the other ranks wait at a CPU-side barrier with their GPUs idle."""
+    out = None
+    if rank == 0:
+        out = {"parity": True}
+        m = 1 << 20
+        host = make_host_data(np, m * world, seed=4242)
+        host[5] = -np.inf
+        host[m * (world - 1) + 11] = -np.inf       # duplicate min in the first and the last shard
+        host[17] = np.inf
+        host[m * (world - 1) + 3] = np.inf
+        with_nan = host.copy()
+        with_nan[m * (world - 1) + 100] = np.nan
+        with_nan[m + 9 if world > 1 else 9] = np.nan
+        for mode_name in ("peer", "nccl"):
+            os.environ["AMM_SHARDED_EXCHANGE"] = mode_name
+            rep = {}
+            try:
+                def shards_of(arr, lens):
+                    res, o = [], 0
+                    for g, ln in enumerate(lens):
+                        t = torch.from_numpy(arr[o:o + ln].copy()).to(f"cuda:{g}") if ln else \
+                            torch.empty(0, dtype=torch.float32, device=f"cuda:{g}")
+                        res.append(amm.DeviceSlice.from_torch(t, dtype="f32") if ln else amm.DeviceSlice(0, 0, "f32", g))
+                        o += ln
+                    return res
+                even = [m] * world
+                ragged = [m] * world
+                ragged[world // 2 if world > 2 else world - 1] = 0      # an empty shard
+                ragged[0] = m * world - sum(ragged[1:])
+                for label, arr, lens, mode in (("dup_extremes", host, even, 0), ("nan_return", with_nan, even, 1),
+                                               ("nan_ignore", with_nan, even, 0), ("empty_shard", host, ragged, 0)):
+                    sh = amm.ShardedDeviceSlice(shards_of(arr, lens))
+                    got = sh.nanargminmax() if mode else sh.argminmax()
+                    exp = oracle.argminmax(arr, mode)
+                    rep[label] = {"ok": tuple(got) == tuple(exp), "got": list(got), "expected": list(exp)}
+                    rep["uses_peer"], rep["uses_nccl"] = sh.uses_peer_exchange, sh.uses_nccl
+                    if label == "dup_extremes":
+                        for _ in range(20):
+                            sh.argminmax()
+                        t0 = time.perf_counter()
+                        for _ in range(200):
+                            sh.argminmax()
+                        rep["us_per_call"] = round((time.perf_counter() - t0) / 200 * 1e6, 2)
+                    sh.close()
+                    out["parity"] = out["parity"] and rep[label]["ok"]
+            except Exception as e:  # noqa: BLE001 - reported, and fails the run below
+                rep["error"] = f"{type(e).__name__}: {e}"
+                out["parity"] = False
+            out[mode_name] = rep
+        os.environ.pop("AMM_SHARDED_EXCHANGE", None)
+        out["us_per_call"] = out.get("peer", {}).get("us_per_call")
+        out["what"] = (f"rank 0 alone, one host thread, {world} GPUs x 2^20 f32 per call, answers vs oracle.argminmax over "
+                       "the concatenated host array")
+    dist.barrier(group=host_group)
+    if rank == 0 and not out["parity"]:
+        raise SystemExit(f"in-process sharded parity failed: {json.dumps(out)}")
+    return out
 
 
 if __name__ == "__main__":

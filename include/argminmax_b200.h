@@ -84,7 +84,7 @@ typedef struct amm_record {
   uint64_t nan_idx; /* index of the first NaN, UINT64_MAX if none seen           */
   uint64_t flags;   /* AMM_REC_HAS_VALUE | AMM_REC_HAS_NAN                        */
   uint64_t n;       /* elements scanned for this record                          */
-  uint64_t seq;     /* workspace call counter (written last)                     */
+  uint64_t seq;     /* workspace call counter                                    */
 } amm_record;
 #define AMM_REC_HAS_VALUE 1ull /* at least one non-NaN element (always set for ints) */
 #define AMM_REC_HAS_NAN 2ull
@@ -174,25 +174,40 @@ int amm_combine_records_launch(const void* dev_records, int count, int mode, amm
 
 /* ------------------------------- fused scan + cross-GPU exchange (one rank per GPU) */
 /*
- * One kernel per rank does the scan AND the collective: its last CTA stores the rank's
+ * One kernel per rank does the scan AND the collective: warp 0 of its last CTA stores the rank's
  * 64-byte record into every peer's exchange buffer over NVLink (peer-mapped memory), waits
  * until all `world` records of the call have landed in its own buffer, folds them (ascending
  * rank order, strict compares) and publishes the GLOBAL record; amm_workspace_wait() then
  * returns the global (argmin, argmax) on every rank.  No NCCL call and no second launch sits
- * on the per-call path.  Setup, once per workspace:
+ * on the per-call path.  Setup, once per workspace (a workspace holds at most ONE exchange;
+ * creating a second one fails with AMM_ERR_ARG until amm_exchange_destroy):
  *   amm_exchange_create   allocates this rank's buffer; `ipc_handle_out` (64 bytes, may be
  *                         NULL in a single process) receives its cudaIpcMemHandle_t;
  *   amm_exchange_connect_ipc   other processes: all ranks' handles (world x 64 B, rank order),
- *                         e.g. gathered once with torch.distributed / MPI;
+ *                         e.g. gathered once with torch.distributed / MPI; `device_ids`
+ *                         (world x 16 bytes, rank order, may be NULL) are the ranks' GPU UUIDs
+ *                         (amm_device_uuid): two ranks on one GPU are refused (AMM_ERR_ARG),
+ *                         because their kernels would spin-wait for each other on one device;
  *   amm_exchange_connect_ptrs  same process: the peers' buffer pointers (peer access enabled).
  * Every rank must issue the same sequence of amm_argminmax_launch_exchange calls (it is a
- * collective); a shard may be empty (n == 0).  A rank that never arrives makes the others
- * fail with AMM_ERR_PEER after ~4 s instead of hanging.  Each rank needs its own GPU.
+ * collective); a shard may be empty (n == 0).
+ * Failure is collective: a rank that waits longer than the timeout (amm_exchange_set_timeout,
+ * default 60 000 ms, AMM_PEER_TIMEOUT_MS; 0 = wait for ever like NCCL) for a peer's record
+ * poisons its own slot in every peer's buffer, so late ranks fail with AMM_ERR_PEER as well
+ * instead of completing on their own.  After AMM_ERR_PEER the exchange is unusable (every
+ * further launch returns AMM_ERR_PEER) until it is destroyed and created again on all ranks.
+ * Teardown across processes: every rank calls amm_exchange_disconnect (closes the imported
+ * handles), then -- after a barrier of the caller's -- amm_exchange_destroy (frees its own
+ * buffer); amm_workspace_destroy does both for a single process.
  */
 int amm_exchange_create(amm_workspace* ws, int world, int rank, void* ipc_handle_out);
-int amm_exchange_connect_ipc(amm_workspace* ws, const void* ipc_handles);
+int amm_exchange_connect_ipc(amm_workspace* ws, const void* ipc_handles, const void* device_ids);
 int amm_exchange_connect_ptrs(amm_workspace* ws, void* const* peer_buffers);
 int amm_exchange_local_buffer(amm_workspace* ws, void** dev_ptr);
+int amm_exchange_set_timeout(amm_workspace* ws, uint64_t milliseconds);
+int amm_exchange_disconnect(amm_workspace* ws);
+int amm_exchange_destroy(amm_workspace* ws);
+int amm_device_uuid(int device, void* uuid_out /* 16 bytes */);
 int amm_argminmax_launch_exchange(int dtype, const void* dev_ptr, uint64_t n, int mode,
                                   uint64_t global_offset, amm_workspace* ws, void* stream);
 
@@ -214,9 +229,18 @@ int amm_host_argminmax_record(int dtype, const void* host_ptr, uint64_t n, int m
 /*
  * ShardedDeviceSlice<T>: one process drives `ngpu` devices of one box.  Shard g
  * is `shard_lens[g]` elements at `dev_ptrs[g]` on `devices[g]`; shards are
- * consecutive index ranges of one logical array.  Each device scans its shard
- * (same kernel), the 64-byte records are exchanged with ONE ncclAllGather over
- * NVLink on the compute streams, then combined as in amm_combine_records.
+ * consecutive index ranges of one logical array (an empty shard is allowed).  All shards are
+ * validated before anything is launched.  Data path, chosen at create time:
+ *   "peer" (default when the devices are distinct and mutually P2P-capable): ONE kernel per
+ *       device = scan + in-kernel exchange of the 64-byte records over NVLink + fold
+ *       (amm_exchange_*, see above); no NCCL call, no second launch;
+ *   "nccl" (north_star's baseline; AMM_SHARDED_EXCHANGE=nccl, and the fallback when peer
+ *       mapping is unavailable): scan kernel -> ONE ncclAllGather of the records on the compute
+ *       streams -> host fold as in amm_combine_records;
+ *   "host" (no NCCL in the process): the records are read from each device's pinned slot.
+ * If a launch fails half way through the devices of a peer-mode call, the kernels already
+ * running are released (their missing peers' slots are filled with poisoned records), the
+ * call returns the error and the handle continues on the nccl / host path.
  */
 int amm_sharded_create(int ngpu, const int* devices, amm_sharded** sh);
 int amm_sharded_destroy(amm_sharded* sh);
@@ -273,7 +297,10 @@ int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, in
    the streaming phase of scan k+1 may start while scan k's last CTA is still folding /
    publishing (programmatic dependent launch).  The caller promises that the input of a scan is
    NOT produced by the kernel enqueued immediately before it on the same stream (memcpys and
-   earlier kernels are fine).  Off by default; results and their order are unchanged. */
+   earlier kernels are fine).  Off by default; results and their order are unchanged.  In the
+   default mode a scan waits for the preceding kernel to complete before its first load and
+   only then lets its own dependents start, so a producer kernel that itself uses programmatic
+   dependent launch (and triggers early) is safe. */
 int amm_workspace_set_pipelined(amm_workspace* ws, int on);
 /* Small inputs take the one-pass latency kernel (exact per-element tracking, no second phase)
    instead of the streaming kernel: by default up to 2^20 elements for 1/2/4-byte dtypes and
@@ -296,6 +323,11 @@ int amm_debug_plan_window_chunks(const uint64_t* begins, const uint64_t* ends, u
                                  size_t elem_size, int sm_count, int chunks_per_sm,
                                  uint64_t* cuts_out, uint64_t cuts_capacity, uint64_t* n_cuts,
                                  uint64_t* first_out);
+/* Debug twin built with -DAMM_PHASE_STAMPS only (tools/phase_stamps.py): %globaltimer stamps of
+   the most recent scan, 8 words per CTA (entry, first tile folded, streaming done, CTA reduced,
+   ticket taken; last CTA: grid folded, exact finish done, published).  The product library
+   returns AMM_ERR_ARG. */
+int amm_debug_read_stamps(amm_workspace* ws, uint64_t* out, int ctas);
 /* grid size and kernels launched by the most recent amm_argminmax_launch on ws */
 int amm_workspace_last_launch(const amm_workspace* ws, int* grid, int* threads, uint64_t* launches_total);
 

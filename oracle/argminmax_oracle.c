@@ -413,3 +413,30 @@ int oracle_argmax(int dtype, const void* arr, uint64_t n, int mode, uint64_t* ou
     default: return 2;
   }
 }
+
+/* Batch form for the windowed tests (the reference has no windowed entry point: its
+ * down-sampling users call `argminmax` once per bin, and so does this loop).  Window w is
+ * [offsets[w], offsets[w+1]) when `offsets` is given, else [w*window, min(n,(w+1)*window)).
+ * out[2w], out[2w+1] = absolute (argmin, argmax); an empty window yields UINT64_MAX twice. */
+static const uint64_t elem_size_of[11] = {1, 2, 4, 8, 1, 2, 4, 8, 2, 4, 8};
+int oracle_argminmax_windows(int dtype, const void* arr, uint64_t n, const uint64_t* offsets,
+                             uint64_t window, uint64_t n_windows, int mode, uint64_t* out) {
+  if (dtype < 0 || dtype > 10) return 2;
+  const uint64_t es = elem_size_of[dtype];
+  for (uint64_t w = 0; w < n_windows; ++w) {
+    uint64_t b = offsets ? offsets[w] : w * window;
+    uint64_t e = offsets ? offsets[w + 1] : b + window;
+    if (e > n) e = n;
+    if (b > e) b = e;
+    if (b == e) {
+      out[2 * w] = out[2 * w + 1] = UINT64_MAX;
+      continue;
+    }
+    uint64_t r[2];
+    const int rc = oracle_argminmax(dtype, (const char*)arr + b * es, e - b, mode, r);
+    if (rc) return rc;
+    out[2 * w] = r[0] + b;
+    out[2 * w + 1] = r[1] + b;
+  }
+  return 0;
+}

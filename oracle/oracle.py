@@ -66,6 +66,9 @@ def _load():
             f.restype = ctypes.c_int
             f.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int,
                           ctypes.POINTER(ctypes.c_uint64)]
+        _lib.oracle_argminmax_windows.restype = ctypes.c_int
+        _lib.oracle_argminmax_windows.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p,
+                                                  ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p]
     return _lib
 
 
@@ -106,6 +109,26 @@ def argminmax(arr: np.ndarray, mode: int = IGNORE_NAN) -> tuple[int, int]:
     if rc:
         raise RuntimeError(f"oracle error {rc}")
     return int(out[0]), int(out[1])
+
+
+def argminmax_windows(arr: np.ndarray, windows, mode: int = IGNORE_NAN) -> np.ndarray:
+    """(n_windows, 2) int64 array of absolute (argmin, argmax) per window -- `argminmax` called
+    once per window, in C.  `windows`: an int (fixed length, last window may be short) or an
+    array of n_windows + 1 ascending offsets.  Empty windows give -1."""
+    arr, code = _prep(arr)
+    if isinstance(windows, (int, np.integer)):
+        nwin = -(-arr.size // int(windows))
+        offs, window = None, int(windows)
+    else:
+        offs = np.ascontiguousarray(windows, dtype=np.uint64)
+        nwin, window = offs.size - 1, 0
+    out = np.empty((nwin, 2), dtype=np.uint64)
+    rc = _load().oracle_argminmax_windows(code, arr.ctypes.data, arr.size,
+                                          offs.ctypes.data if offs is not None else None, window, nwin, mode,
+                                          out.ctypes.data)
+    if rc:
+        raise RuntimeError(f"oracle error {rc}")
+    return out.view(np.int64)
 
 
 def argmin(arr: np.ndarray, mode: int = IGNORE_NAN) -> int:

@@ -118,6 +118,38 @@ def test_f32_1g_planted_and_shard_decomposition():
 
 
 @pytest.mark.slow
+def test_f32_1g_full_oracle_pass():
+    """config 4 as bench.py times it (f32 x 2^30 uniform random bit patterns, NaN -> 0): a FULL
+    pass of the scalar oracle and of the restated dispatched SIMD path over the same 4 GiB, both
+    semantics, then with NaNs and duplicate extremes injected.  ~10 s of CPU per oracle pass."""
+    import torch
+
+    from argminmax_b200 import DeviceSlice
+    n = 1 << 30
+    rng = np.random.default_rng(2026)
+    a = rng.integers(0, 2**32, n, dtype=np.uint32).view(np.float32)
+    a[np.isnan(a)] = 0
+    t = torch.empty(n, dtype=torch.float32, device="cuda:0")
+    t.copy_(torch.from_numpy(a))
+    ds = DeviceSlice.from_torch(t)
+    exp = oracle.argminmax(a, 0)
+    assert ds.argminmax() == exp
+    assert oracle.cpu_simd_argminmax_f32(a) == exp          # the reference's SIMD path agrees
+    assert ds.nanargminmax() == oracle.argminmax(a, 1) == exp  # no NaN: both semantics coincide
+    # duplicate the extremes LATER in the array (first occurrence must still win), a NaN far out
+    lo, hi = exp
+    dup_lo, dup_hi, nan_at = n - 12_345, n - 3, 987_654_321
+    for arr_idx, src in ((dup_lo, lo), (dup_hi, hi)):
+        a[arr_idx] = a[src]
+        t[arr_idx] = t[src]
+    a[nan_at] = np.nan
+    t[nan_at] = float("nan")
+    torch.cuda.synchronize()
+    assert ds.argminmax() == oracle.argminmax(a, 0) == exp
+    assert ds.nanargminmax() == oracle.argminmax(a, 1) == (nan_at, nan_at)
+
+
+@pytest.mark.slow
 def test_indices_beyond_2_pow_32():
     """config 5 needs 64-bit global indices (16 Gi elements per GPU at 2 GPUs): a u8 array of
     2^32 + 2^20 + 5 elements with the extremes planted past index 2^32."""

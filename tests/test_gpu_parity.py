@@ -35,7 +35,8 @@ def test_reference_known_answers(v, arr):
 
 
 SIZES = [1, 2, 3, 4, 5, 7, 8, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 129, 255, 257, 1000, 1027,
-         4095, 4096, 4097, 8193, 32768, 65535, 65537, 131072, 1 << 20, (1 << 20) + 3, 3_000_017]
+         4095, 4096, 4097, 8193, 32768, 65535, 65537, 131072, 1 << 20, (1 << 20) + 3, 3_000_017,
+         10_000_019]
 
 
 @pytest.mark.parametrize("dt", G.ALL_DTYPES)
@@ -84,6 +85,30 @@ def test_narrow_types_many_duplicates(dt):
         a = random_array(dt, n, rng)
         for mode in modes_for(dt):
             assert_parity(a, mode, what="dups")
+
+
+@pytest.mark.parametrize("dt", G.ALL_DTYPES)
+def test_few_distinct_values_every_partition(dt):
+    """Arrays of 2-3 distinct values: EVERY tile, every CTA and both the pre-assigned and the
+    claimed (dynamic) part of the tile sequence hold copies of both extremes, so any level that
+    breaks a tie the wrong way (later tile, later CTA, claimed tile before static tile, partial
+    tile before full tile) shows up as a wrong index.  First occurrences sit at odd places."""
+    rng = np.random.default_rng(4242)
+    T = G.NP[dt]
+    for n in (700_001, 3_000_017):
+        a = np.full(n, 5, dtype=T)
+        a[rng.integers(0, n, n // 3)] = 7
+        a[rng.integers(0, n, n // 3)] = 3
+        first = 1 + int(rng.integers(0, 40))
+        a[:first] = 5                       # neither extreme before `first`
+        a[first] = 3
+        a[first + 1] = 7
+        for mode in modes_for(dt):
+            got = assert_parity(a, mode, what="few-values")
+            assert got == (first, first + 1)
+    a = np.full(2_000_003, 9, dtype=T)      # all equal: (0, 0) on every path
+    for mode in modes_for(dt):
+        assert assert_parity(a, mode, what="all-equal") == (0, 0)
 
 
 @pytest.mark.parametrize("dt", G.ALL_DTYPES)
