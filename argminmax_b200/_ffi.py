@@ -101,6 +101,7 @@ SIGNATURES = {
     "amm_variant_count": (_i, []),
     "amm_variant_name": (ctypes.c_char_p, [_i]),
     "amm_measure_call_latency": (_i, [_i, _vp, _u64, _i, _vp, _vp, _i, ctypes.POINTER(ctypes.c_double)]),
+    "amm_measure_exchange_latency": (_i, [_i, _vp, _u64, _i, _u64, _vp, _vp, _i, ctypes.POINTER(ctypes.c_double)]),
     "amm_workspace_last_launch": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), _u64p]),
     "amm_debug_plan_window_chunks": (_i, [_u64p, _u64p, _u64, ctypes.c_size_t, _i, _i, _u64p, _u64, _u64p,
                                           _u64p]),

@@ -83,24 +83,21 @@ struct amm_workspace {
 namespace amm {
 // Every public entry point leaves the caller's current CUDA device as it found it.
 struct DeviceGuard {
-  int prev = -1;
+  int orig = -1;  // the caller's current device
   int rc = AMM_OK;
   explicit DeviceGuard(int device) {
-    int cur = -1;
-    if (cudaGetDevice(&cur) != cudaSuccess) {
+    if (cudaGetDevice(&orig) != cudaSuccess) {
+      orig = -1;
       rc = AMM_ERR_CUDA;
       return;
     }
-    if (cur != device) {
-      if (cudaSetDevice(device) != cudaSuccess) {
-        rc = AMM_ERR_CUDA;
-        return;
-      }
-      prev = cur;
-    }
+    if (orig != device && cudaSetDevice(device) != cudaSuccess) rc = AMM_ERR_CUDA;
   }
+  // restores the caller's device whatever the guarded code made current in between (functions
+  // that walk over several devices call set_device() inside the guard)
   ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
+    int now = -1;
+    if (orig >= 0 && cudaGetDevice(&now) == cudaSuccess && now != orig) cudaSetDevice(orig);
   }
   DeviceGuard(const DeviceGuard&) = delete;
   DeviceGuard& operator=(const DeviceGuard&) = delete;

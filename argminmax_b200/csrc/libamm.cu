@@ -997,6 +997,37 @@ int amm_debug_read_stamps(amm_workspace* ws, uint64_t* out, int ctas) {
   return AMM_OK;
 }
 
+/* The same for the collective call (amm_argminmax_launch_exchange + amm_workspace_wait): every
+   rank of the exchange must call it with the same `calls`. */
+int amm_measure_exchange_latency(int dtype, const void* dev_ptr, uint64_t n, int mode,
+                                 uint64_t global_offset, amm_workspace* ws, void* stream, int calls,
+                                 double out_us[3]) {
+  if (!out_us || calls < 1) return AMM_ERR_ARG;
+  uint64_t r[2];
+  auto once = [&]() -> int {
+    int rc = launch(dtype, dev_ptr, n, mode, global_offset, ws, (cudaStream_t)stream, nullptr, true);
+    if (rc) return rc;
+    return amm_workspace_wait(ws, stream, mode, r);
+  };
+  for (int i = 0; i < calls / 10 + 10; ++i) {
+    int rc = once();
+    if (rc) return rc;
+  }
+  std::vector<double> us((size_t)calls);
+  for (int i = 0; i < calls; ++i) {
+    const auto t0 = std::chrono::steady_clock::now();
+    int rc = once();
+    const auto t1 = std::chrono::steady_clock::now();
+    if (rc) return rc;
+    us[(size_t)i] = std::chrono::duration<double, std::micro>(t1 - t0).count();
+  }
+  std::sort(us.begin(), us.end());
+  out_us[0] = us[us.size() / 2];
+  out_us[1] = us[0];
+  out_us[2] = us[us.size() * 99 / 100];
+  return AMM_OK;
+}
+
 const char* amm_status_string(int status) {
   switch (status) {
     case AMM_OK: return "ok";

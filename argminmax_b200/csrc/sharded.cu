@@ -20,7 +20,11 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 
 #include "amm_internal.h"
 
@@ -59,6 +63,33 @@ constexpr int kMaxGpus = 16;
 
 }  // namespace
 
+struct amm_sharded;
+
+// One launcher thread per device (devices 1..G-1; the caller's thread drives device 0).  A call
+// on the fused peer path is G x (set device, launch, wait for the pinned slot): from ONE host
+// thread the G launches alone cost G x ~3 us (35 us per call at 8 GPUs, profiles/r01c_scaling.md)
+// although the kernels themselves overlap; with a thread per device they go out together.
+// A worker spins for ~100 us after its last job (a tight loop of calls never sleeps), then parks
+// on a condition variable.
+struct ShardWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<uint64_t> go{0};     // job sequence number posted by the caller
+  std::atomic<uint64_t> done{0};   // ... and completed by the worker
+  std::atomic<bool> parked{false};
+  std::atomic<bool> quit{false};
+  amm_sharded* sh = nullptr;
+  int g = 0;
+  // job
+  int dtype = 0, mode = 0;
+  const void* ptr = nullptr;
+  uint64_t n = 0, offset = 0;
+  // result
+  int rc = 0;
+  uint64_t out[2] = {0, 0};
+};
+
 struct amm_sharded {
   int ngpu;
   int devices[kMaxGpus];
@@ -70,15 +101,32 @@ struct amm_sharded {
   bool use_peer;  // fused in-kernel exchange over peer-mapped memory (default when possible)
   NcclApi api;
   ncclComm_t comms[kMaxGpus];
+  ShardWorker* workers[kMaxGpus];  // [0] unused; nullptr = the caller's thread drives that device
+  uint64_t job_seq;
 };
 
 using namespace amm;
 
 extern "C" {
 
+static void start_workers(amm_sharded* sh);
+
 int amm_sharded_destroy(amm_sharded* sh) {
   if (!sh) return AMM_OK;
   DeviceGuard restore(sh->devices[0]);  // the per-device set_device calls below are undone on exit
+  for (int g = 1; g < sh->ngpu; ++g) {
+    ShardWorker* w = sh->workers[g];
+    if (!w) continue;
+    w->quit.store(true);
+    {
+      std::lock_guard<std::mutex> lk(w->mu);
+      w->go.fetch_add(1);
+    }
+    w->cv.notify_one();
+    if (w->th.joinable()) w->th.join();
+    delete w;
+    sh->workers[g] = nullptr;
+  }
   for (int g = 0; g < sh->ngpu; ++g) {
     set_device(sh->devices[g]);
     if (sh->streams[g]) {
@@ -164,6 +212,7 @@ int amm_sharded_create(int ngpu, const int* devices, amm_sharded** out) {
         if (amm_exchange_connect_ptrs(sh->ws[a], bufs) != AMM_OK) ok = false;
       (void)cudaGetLastError();
       sh->use_peer = ok;
+      if (ok) start_workers(sh);
     }
   }
   sh->use_nccl = false;
@@ -187,42 +236,78 @@ int amm_sharded_workspace(amm_sharded* sh, int g, amm_workspace** ws) {
   return AMM_OK;
 }
 
-// A peer-mode call whose launch loop stopped at device `failed`: the kernels already running on
-// devices [0, failed) wait for records that will never be sent.  Release them by writing a
-// poisoned record (AMM_REC_PEER_TIMEOUT, this call's tag) for every missing rank into their
-// exchange buffers, drain their streams, and take the handle off the peer path for good.
-static void abort_peer_call(amm_sharded* sh, int failed) {
-  for (int a = 0; a < failed; ++a) {
-    amm_workspace* ws = sh->ws[a];
-    if (set_device(sh->devices[a]) != AMM_OK) continue;
-    const uint64_t xseq = ws->xseq;  // the tag the running kernel waits for
-    const uint64_t bank = (xseq & 1ull) * (uint64_t)sh->ngpu;
-    for (int r = failed; r < sh->ngpu; ++r) {
-      uint64_t slot[XCHG_SLOT_WORDS];
-      memset(slot, 0, sizeof(slot));
-      amm_record rec;
-      memset(&rec, 0, sizeof(rec));
-      rec.min_idx = rec.max_idx = rec.nan_idx = AMM_NO_INDEX;
-      rec.flags = AMM_REC_PEER_TIMEOUT;
-      memcpy(slot, &rec, sizeof(rec));
-      slot[8] = mix_checksum(slot, PEER_SLOT_SEED ^ xseq);
-      slot[9] = xseq;
-      // default-stream copy: the per-device streams are non-blocking, so this does not queue
-      // behind the spinning kernel
-      cudaMemcpy(ws->xbuf + (bank + (uint64_t)r) * XCHG_SLOT_WORDS, slot, sizeof(slot),
-                 cudaMemcpyHostToDevice);
-    }
-  }
-  for (int a = 0; a < failed; ++a) {
-    if (set_device(sh->devices[a]) != AMM_OK) continue;
-    cudaStreamSynchronize(sh->streams[a]);
-    sh->ws[a]->xbroken = 1;
+// A peer-mode call in which rank `missing` could not launch: the kernels of the other devices wait
+// for a record that will never be sent.  Release them by writing a poisoned record
+// (AMM_REC_PEER_TIMEOUT, this call's tag) into rank `missing`'s slot of every other device's
+// exchange buffer; their waits then return AMM_ERR_PEER and mark the exchange broken.
+static void poison_as_missing_rank(amm_sharded* sh, int missing) {
+  const uint64_t xseq = sh->ws[missing]->xseq + 1;  // the tag of the call that did not go out here
+  const uint64_t bank = (xseq & 1ull) * (uint64_t)sh->ngpu;
+  uint64_t slot[XCHG_SLOT_WORDS];
+  memset(slot, 0, sizeof(slot));
+  amm_record rec;
+  memset(&rec, 0, sizeof(rec));
+  rec.min_idx = rec.max_idx = rec.nan_idx = AMM_NO_INDEX;
+  rec.flags = AMM_REC_PEER_TIMEOUT;
+  memcpy(slot, &rec, sizeof(rec));
+  slot[8] = mix_checksum(slot, PEER_SLOT_SEED ^ xseq);
+  slot[9] = xseq;
+  for (int a = 0; a < sh->ngpu; ++a) {
+    if (a == missing || !sh->ws[a]->xbuf) continue;
+    // legacy-default-stream copy (UVA: any current device): the per-device streams are
+    // non-blocking, so this does not queue behind the spinning kernel
+    cudaMemcpy(sh->ws[a]->xbuf + (bank + (uint64_t)missing) * XCHG_SLOT_WORDS, slot, sizeof(slot),
+               cudaMemcpyHostToDevice);
   }
   (void)cudaGetLastError();
-  sh->use_peer = false;
-  if (!sh->use_nccl && sh->api.CommInitAll == nullptr && load_nccl(sh->api) &&
-      sh->api.CommInitAll(sh->comms, sh->ngpu, sh->devices) == 0)
-    sh->use_nccl = true;
+}
+
+// one device's part of a peer-mode call: launch the fused kernel, wait for the global answer
+static int peer_job(amm_sharded* sh, int g, int dtype, const void* ptr, uint64_t n, int mode,
+                    uint64_t offset, uint64_t out[2]) {
+  int rc = launch(dtype, ptr, n, mode, offset, sh->ws[g], sh->streams[g], nullptr, true);
+  if (rc) {  // (a CUDA launch error; arguments were checked before anything was launched)
+    poison_as_missing_rank(sh, g);
+    return rc;
+  }
+  return amm_workspace_wait(sh->ws[g], sh->streams[g], mode, out);
+}
+
+static void worker_main(ShardWorker* w) {
+  cudaSetDevice(w->sh->devices[w->g]);
+  uint64_t seen = 0;
+  for (;;) {
+    int spins = 0;
+    while (w->go.load() == seen) {
+      if (++spins > 4000) {  // ~100 us of polling, then sleep until the next call
+        std::unique_lock<std::mutex> lk(w->mu);
+        w->parked.store(true);
+        w->cv.wait(lk, [&] { return w->go.load() != seen; });
+        w->parked.store(false);
+        break;
+      }
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    if (w->quit.load()) return;
+    seen = w->go.load();
+    w->rc = peer_job(w->sh, w->g, w->dtype, w->ptr, w->n, w->mode, w->offset, w->out);
+    w->done.store(seen);
+  }
+}
+
+static void start_workers(amm_sharded* sh) {
+  const char* env = getenv("AMM_SHARDED_THREADS");
+  if (env && atoi(env) == 0) return;
+  for (int g = 1; g < sh->ngpu; ++g) {
+    ShardWorker* w = new (std::nothrow) ShardWorker();
+    if (!w) return;
+    w->sh = sh;
+    w->g = g;
+    sh->workers[g] = w;
+    w->th = std::thread(worker_main, w);
+  }
 }
 
 int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptrs,
@@ -239,40 +324,85 @@ int amm_sharded_argminmax(amm_sharded* sh, int dtype, const void* const* dev_ptr
   }
   if (total == 0) return AMM_ERR_EMPTY;
   if (sh->use_peer) {
-    // fused path: one kernel per device does scan + exchange + combine
-    uint64_t off = 0;
-    for (int g = 0; g < sh->ngpu; ++g) {
-      int rc = launch(dtype, dev_ptrs[g], shard_lens[g], mode, off, sh->ws[g], sh->streams[g],
-                      nullptr, true);
-      if (rc) {  // (a CUDA launch error; arguments were checked above)
-        abort_peer_call(sh, g);
-        return rc;
+    // fused path: one kernel per device does scan + exchange + combine; devices 1..G-1 are
+    // driven by their launcher threads, device 0 by this thread
+    const uint64_t job = ++sh->job_seq;
+    uint64_t off = shard_lens[0];
+    int rcs[kMaxGpus];
+    uint64_t res[kMaxGpus][2];
+    memset(res, 0, sizeof(res));
+    for (int g = 1; g < sh->ngpu; ++g) {
+      ShardWorker* w = sh->workers[g];
+      if (w) {
+        w->dtype = dtype;
+        w->mode = mode;
+        w->ptr = dev_ptrs[g];
+        w->n = shard_lens[g];
+        w->offset = off;
+        w->go.store(job);
+        if (w->parked.load()) {
+          std::lock_guard<std::mutex> lk(w->mu);
+          w->cv.notify_one();
+        }
       }
       off += shard_lens[g];
     }
-    uint64_t first[2] = {0, 0};
+    if (sh->workers[1] == nullptr && sh->ngpu > 1) {
+      // no launcher threads (AMM_SHARDED_THREADS=0): launch everything, then wait for everything
+      uint64_t o = 0;
+      int failed = -1;
+      for (int g = 0; g < sh->ngpu && failed < 0; ++g) {
+        rcs[g] = launch(dtype, dev_ptrs[g], shard_lens[g], mode, o, sh->ws[g], sh->streams[g], nullptr, true);
+        if (rcs[g]) {
+          poison_as_missing_rank(sh, g);
+          failed = g;
+        }
+        o += shard_lens[g];
+      }
+      for (int g = 0; g < sh->ngpu; ++g) {
+        if (failed >= 0 && g >= failed) {
+          if (g > failed) rcs[g] = AMM_ERR_PEER;
+          continue;
+        }
+        rcs[g] = set_device(sh->devices[g]);
+        if (rcs[g] == AMM_OK) rcs[g] = amm_workspace_wait(sh->ws[g], sh->streams[g], mode, res[g]);
+      }
+    } else {
+      set_device(sh->devices[0]);
+      rcs[0] = peer_job(sh, 0, dtype, dev_ptrs[0], shard_lens[0], mode, 0, res[0]);
+      for (int g = 1; g < sh->ngpu; ++g) {
+        ShardWorker* w = sh->workers[g];
+        while (w->done.load() != job) {
+#if defined(__x86_64__)
+          __builtin_ia32_pause();
+#endif
+        }
+        rcs[g] = w->rc;
+        res[g][0] = w->out[0];
+        res[g][1] = w->out[1];
+      }
+    }
     int status = AMM_OK;
-    for (int g = 0; g < sh->ngpu; ++g) {  // wait for ALL devices even if one reports an error
-      uint64_t r[2] = {0, 0};
-      int rc = set_device(sh->devices[g]);
-      if (rc == AMM_OK) rc = amm_workspace_wait(sh->ws[g], sh->streams[g], mode, r);
-      if (rc) {
-        if (status == AMM_OK) status = rc;
-        continue;
-      }
-      if (g == 0) {
-        first[0] = r[0];
-        first[1] = r[1];
-      } else if (status == AMM_OK && (r[0] != first[0] || r[1] != first[1])) {
-        status = AMM_ERR_PEER;  // every device must have folded the same table
-      }
+    for (int g = 0; g < sh->ngpu; ++g) {
+      if (rcs[g] != AMM_OK && (status == AMM_OK || status == AMM_ERR_PEER)) status = rcs[g];
+      // every device must have folded the same table
+      if (status == AMM_OK && (res[g][0] != res[0][0] || res[g][1] != res[0][1])) status = AMM_ERR_PEER;
     }
     if (status != AMM_OK) {
-      if (status == AMM_ERR_PEER) abort_peer_call(sh, 0);  // nothing left running: just leave the peer path
+      // the exchange is out of step (or a device is in trouble): leave the peer path for good
+      for (int g = 0; g < sh->ngpu; ++g) {
+        if (set_device(sh->devices[g]) == AMM_OK) cudaStreamSynchronize(sh->streams[g]);
+        sh->ws[g]->xbroken = 1;
+      }
+      (void)cudaGetLastError();
+      sh->use_peer = false;
+      if (!sh->use_nccl && sh->api.CommInitAll == nullptr && load_nccl(sh->api) &&
+          sh->api.CommInitAll(sh->comms, sh->ngpu, sh->devices) == 0)
+        sh->use_nccl = true;
       return status;
     }
-    out[0] = first[0];
-    out[1] = first[1];
+    out[0] = res[0][0];
+    out[1] = res[0][1];
     return AMM_OK;
   }
   // 1. every device scans its shard (async, one stream per device)

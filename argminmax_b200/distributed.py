@@ -57,7 +57,7 @@ def combine_across_ranks(local: _ffi.AmmRecord, mode: int, group=None) -> tuple[
 
 
 # workspaces that currently hold a peer exchange (a workspace holds at most one)
-_exchange_owners: dict[int, "DistributedShardedSlice"] = {}
+_exchange_owners: dict[int, "DistributedShardedSlice"] = {}  # keyed by the amm_workspace handle
 
 
 class DistributedShardedSlice:
@@ -109,7 +109,7 @@ class DistributedShardedSlice:
 
         from .device_slice import Workspace
 
-        if id(self._ws) in _exchange_owners:  # the shard's workspace already carries an exchange
+        if self._ws.handle.value in _exchange_owners:  # the shard's workspace already carries an exchange
             self._ws = Workspace(self.shard.device)
         ws = self._ws
         handle = (ctypes.c_uint8 * 64)()
@@ -134,7 +134,7 @@ class DistributedShardedSlice:
         if int(flag.item()) == 1:
             self.exchange = "peer"
             self._owns_exchange = True
-            _exchange_owners[id(ws)] = self
+            _exchange_owners[ws.handle.value] = self
         elif created:
             # some rank failed: unmap whatever was mapped, then free (same order as close())
             lib().amm_exchange_disconnect(ws.handle)
@@ -153,7 +153,7 @@ class DistributedShardedSlice:
         if not self._owns_exchange:
             return
         self._owns_exchange = False
-        _exchange_owners.pop(id(self._ws), None)
+        _exchange_owners.pop(self._ws.handle.value, None)
         torch.cuda.synchronize(self.shard.device)
         lib().amm_exchange_disconnect(self._ws.handle)
         dist.barrier(group=self.group)

@@ -326,7 +326,7 @@ def run_reference(args) -> int:
         "gpu_launches": 0, "verified_vs_oracle": verified, "result": list(res),
         "where": "host CPU only (the reference has no GPU path); under torchrun rank 0 alone runs",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -436,6 +436,26 @@ def h2d_ceiling(torch, host, device, stream_count: int = 1, reps: int = 3) -> fl
     return best
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout() -> None:
+    """The driver parses ONE JSON line from stdout.  Libraries print there too (NCCL's version
+    banner on communicator creation, for one), so fd 1 is pointed at stderr for the whole run and
+    the line is written to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 # --------------------------------------------------------------------------- main
 def main() -> int:
     ap = argparse.ArgumentParser()
@@ -451,6 +471,7 @@ def main() -> int:
                     help="skip the dtype table, serialised probes, strong scaling, config 5 (ncu runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -629,41 +650,49 @@ def main() -> int:
             sp.workspace.set_pipelined(False)
             # host-visible latency of one synchronous collective call, and where sharding starts
             # to pay: total sizes 2^18 .. 2^30 against the single-GPU call on rank 0's buffer
+            # (timed inside the library: no Python between the calls)
             cross = []
+            out3 = (ctypes.c_double * 3)()
             for lg in (18, 20, 22, 24, 26, 28, 30):
                 tot = 1 << lg
                 pr = tot // world
-                a = amm.DeviceSlice.from_torch(data[:pr], dtype=DTYPE, workspace=ws, stream=stream)
-                sp.shard = a
-                sp.n_total, sp.global_offset = tot, rank * pr
-                one = amm.DeviceSlice.from_torch(data[:tot], dtype=DTYPE, workspace=ws, stream=stream)
-                for _ in range(10):
-                    sp.argminmax()
-                    one.argminmax()
-                barrier()
-                calls = 100
-                t0 = time.perf_counter()
-                for _ in range(calls):
-                    sp.argminmax()
-                us_sh = max_over_ranks((time.perf_counter() - t0) / calls * 1e6)
-                t0 = time.perf_counter()
-                for _ in range(calls):
-                    one.argminmax()
-                us_one = (time.perf_counter() - t0) / calls * 1e6
-                rows1 = gather_rows([us_one])
-                cross.append({"total_elems_log2": lg, "us_sharded": round(us_sh, 2), "us_one_gpu": round(rows1[0][0], 2)})
-            first_win = next((c["total_elems_log2"] for c in cross if c["us_sharded"] < c["us_one_gpu"]), None)
+                us_sh = None
+                if sp.exchange == "peer":
+                    barrier()
+                    rc = amm.lib().amm_measure_exchange_latency(amm.DTYPES[DTYPE], data.data_ptr(), pr, amm.IGNORE_NAN,
+                                                                rank * pr, sp.workspace.handle, stream, 200, out3)
+                    if rc:
+                        raise RuntimeError(f"amm_measure_exchange_latency rc={rc}")
+                    us_sh = max_over_ranks(out3[0])
+                rc = amm.lib().amm_measure_call_latency(amm.DTYPES[DTYPE], data.data_ptr(), tot, amm.IGNORE_NAN,
+                                                        ws.handle, stream, 200, out3)
+                if rc:
+                    raise RuntimeError(f"amm_measure_call_latency rc={rc}")
+                rows1 = gather_rows([out3[0]])
+                cross.append({"total_elems_log2": lg, "us_sharded": round(us_sh, 2) if us_sh is not None else None,
+                              "us_one_gpu": round(rows1[0][0], 2)})
+            first_win = next((c["total_elems_log2"] for c in cross
+                              if c["us_sharded"] is not None and c["us_sharded"] < c["us_one_gpu"]), None)
             sp.close()
+            # this box's single-GPU pipelined time for the whole 2^30 (denominator of the pipelined efficiency)
+            ws.set_pipelined(True)
+            for _ in range(3):
+                shard.launch(amm.IGNORE_NAN)
+            n1_pipe_ms = events_us(torch, lambda i: shard.launch(amm.IGNORE_NAN), 20) / 1e3
+            shard.wait(amm.IGNORE_NAN)
+            ws.set_pipelined(False)
             extras["strong"] = {
                 "total_elems": n, "per_gpu_elems": per, "ms": round(strong_ms, 5),
                 "gbs": round(nbytes / strong_ms / 1e6, 1),
                 "efficiency_vs_n1": round(kernel_ms / (world * strong_ms), 4),
                 "ms_pipelined": round(strong_pipe_ms, 5),
-                "efficiency_vs_n1_pipelined": round(ms_per_step / (world * strong_pipe_ms), 4) if False else None,
-                "n1_ms_same_box": round(kernel_ms, 5),
+                "efficiency_vs_n1_pipelined": round(n1_pipe_ms / (world * strong_pipe_ms), 4),
+                "n1_ms_same_box": round(kernel_ms, 5), "n1_ms_pipelined_same_box": round(n1_pipe_ms, 5),
                 "what": "one logical f32 array of 2^30 elements split over the N GPUs; device time per serialised "
                         "collective call (scan fused with the in-kernel record exchange), max over ranks; "
-                        "efficiency = t(1 GPU, 2^30, serialised) / (N x t(N GPUs))",
+                        "efficiency = t(1 GPU, 2^30, serialised) / (N x t(N GPUs)); sync_call_us_by_total_size: median host "
+                        "wall clock of the synchronous collective call vs the single-GPU call on the same total size, timed "
+                        "inside the library",
                 "sync_call_us_by_total_size": cross, "sharding_pays_from_log2_elems": first_win,
             }
             # ---- config 5: 32 Gi f32 elements (128 GiB) IN TOTAL over the N GPUs: this rank's 4 GiB
@@ -815,7 +844,7 @@ def main() -> int:
             **extras,
             "result": list(result), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         if sharded is not None:
             sharded.close()

@@ -315,6 +315,11 @@ const char* amm_variant_name(int variant);
    (no binding overhead): out_us = {median, min, p99} microseconds over `calls` calls. */
 int amm_measure_call_latency(int dtype, const void* dev_ptr, uint64_t n, int mode,
                              amm_workspace* ws, void* stream, int calls, double out_us[3]);
+/* The same for the collective call of the fused exchange (amm_argminmax_launch_exchange +
+   amm_workspace_wait); every rank must call it with the same `calls`. */
+int amm_measure_exchange_latency(int dtype, const void* dev_ptr, uint64_t n, int mode,
+                                 uint64_t global_offset, amm_workspace* ws, void* stream, int calls,
+                                 double out_us[3]);
 /* Test hook (pure host logic, needs no GPU): the chunk plan the windowed form uses for few
    large adjacent windows.  chunk k = [cuts[k], cuts[k+1]); window w owns chunks
    [first[w], first[w+1]).  `first_out` holds n_windows + 1 entries.  Returns 1000 when the

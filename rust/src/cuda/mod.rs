@@ -230,8 +230,12 @@ pub fn host_argminmax<T: CudaDType>(data: &[T], ws: &Workspace, mode: c_int) -> 
 }
 
 /// One logical array split into consecutive index ranges over the GPUs of one box.  Each GPU
-/// scans its shard, the 64-byte records are exchanged with one NCCL all-gather and combined
-/// with a deterministic first-index tie-break (all inside `amm_sharded_argminmax`).
+/// scans its shard; by default the SAME kernel then exchanges the 64-byte records with its peers
+/// over NVLink (peer-mapped buffers) and folds them with a deterministic first-index tie-break,
+/// so a call is one launch per GPU and no NCCL call.  `AMM_SHARDED_EXCHANGE=nccl` (and boxes
+/// without peer access) use north_star's baseline instead: scan kernels, ONE `ncclAllGather` of
+/// the records, host fold.  All of it happens inside `amm_sharded_argminmax`; every shard is
+/// validated before anything is launched.
 pub struct ShardedDeviceSlice<T: CudaDType> {
     raw: *mut AmmSharded,
     ptrs: Vec<*const c_void>,
