@@ -42,6 +42,10 @@ struct amm_workspace {
   int direct_packed;      // 32-bit keys: packed-word atomics instead of partials (AMM_DIRECT_PACKED=0: off)
   int scan_packed;        // the same cross-CTA step in the streaming kernel (AMM_SCAN_PACKED=0: off)
   int scan_dyn_pct;       // share of the tiles claimed at run time: -1 automatic, 0 none, 1..90 percent (AMM_SCAN_DYN_PCT)
+  int scan_ring;          // TMA-ring kernel: -1 automatic (inputs >= 512 MiB), 0 never, 1 always (AMM_SCAN_RING)
+  int ring_ctas_per_sm;   // ... CTAs per SM (2: 2 x 96 KiB of stages; AMM_RING_CTAS)
+  int ring_ready[AMM_POLICY_SLOTS][4];  // ... dynamic shared memory opted in (per instantiation)
+  int scan_dyn_pipelined; // claimed tail also for pipelined scans (AMM_SCAN_DYN_PIPELINED=0: off)
   int scan_contig;        // tile partition of the streaming kernel: -1 automatic, 0 grid-stride, 1 contiguous ranges
   uint64_t direct_elems32, direct_elems64;  // direct_auto: latency kernel up to this many elements (32- / 64-bit keys)
   int occupancy[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];      // cached CTAs/SM ...
@@ -50,7 +54,8 @@ struct amm_workspace {
   size_t dyn_smem_set[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // MaxDynamicSharedMemorySize set so far
   size_t smem_per_sm, smem_reserved_per_cta, smem_optin_per_cta;  // device limits (co-residency cap)
   void* partials;            // max_grid x 64 B
-  uint32_t* ticket;          // last-block-done counter (self-resetting)
+  uint32_t* ticket;          // 128 words: [0] last-block-done counter (self-resetting), [8] bounds-check
+                             // errors, [16..21] packed candidate words, [64..127] claim-counter ring
   amm_record* rec_dev;       // device record slot
   amm_record* rec_host;      // pinned + mapped host slot: record + checksum word (128 B)
   amm_record* rec_host_dev;  // ... its device address

@@ -184,6 +184,8 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
     p->child[i]->scan_packed = ws->scan_packed;
     p->child[i]->scan_contig = ws->scan_contig;
     p->child[i]->scan_dyn_pct = ws->scan_dyn_pct;
+    p->child[i]->scan_ring = ws->scan_ring;
+    p->child[i]->scan_dyn_pipelined = ws->scan_dyn_pipelined;
     p->child[i]->pdl = ws->pdl;
     p->child[i]->direct_threads = ws->direct_threads;
     p->child[i]->direct_ctas_per_sm = ws->direct_ctas_per_sm;

@@ -321,6 +321,10 @@ static int workspace_init(amm_workspace* ws, int device) {
   ws->scan_packed = getenv("AMM_SCAN_PACKED") ? atoi(getenv("AMM_SCAN_PACKED")) : 1;
   ws->scan_contig = getenv("AMM_SCAN_CONTIG") ? atoi(getenv("AMM_SCAN_CONTIG")) : -1;
   ws->scan_dyn_pct = getenv("AMM_SCAN_DYN_PCT") ? atoi(getenv("AMM_SCAN_DYN_PCT")) : -1;
+  ws->scan_ring = getenv("AMM_SCAN_RING") ? atoi(getenv("AMM_SCAN_RING")) : -1;
+  ws->ring_ctas_per_sm = getenv("AMM_RING_CTAS") ? atoi(getenv("AMM_RING_CTAS")) : 2;
+  if (ws->ring_ctas_per_sm < 1 || ws->ring_ctas_per_sm > 2) ws->ring_ctas_per_sm = 2;
+  ws->scan_dyn_pipelined = getenv("AMM_SCAN_DYN_PIPELINED") ? atoi(getenv("AMM_SCAN_DYN_PIPELINED")) : 1;
   ws->direct_elems32 = getenv("AMM_DIRECT_ELEMS32") ? strtoull(getenv("AMM_DIRECT_ELEMS32"), nullptr, 10) : (1ull << 20);
   ws->direct_elems64 = getenv("AMM_DIRECT_ELEMS64") ? strtoull(getenv("AMM_DIRECT_ELEMS64"), nullptr, 10) : (1ull << 16);
   ws->xtimeout_ms = getenv("AMM_PEER_TIMEOUT_MS") ? strtoull(getenv("AMM_PEER_TIMEOUT_MS"), nullptr, 10) : 60000;
@@ -342,10 +346,10 @@ static int workspace_init(amm_workspace* ws, int device) {
   ws->max_grid = ws->sm_count * 32;
   // partials sized for the widest Best<int64_t> (40 B) -> 64 B slots
   AMM_CUDA(cudaMalloc(&ws->partials, (size_t)ws->max_grid * 64));
-  AMM_CUDA(cudaMalloc((void**)&ws->ticket, 256));
-  AMM_CUDA(cudaMemset(ws->ticket, 0, 256));
+  AMM_CUDA(cudaMalloc((void**)&ws->ticket, 512));
+  AMM_CUDA(cudaMemset(ws->ticket, 0, 512));
   // words of the ticket block: [0] ticket, [8] bounds-check error count, [16..21] packed candidate
-  // words, [24] claim counter of the dynamic tail
+  // words, [64..127] claim counters of the dynamic tail (ring indexed by the call's seq)
   {  // packed candidate words start at their identities (packed_grid_reduce)
     const unsigned long long ident[3] = {PACK_MIN_NONE, PACK_MAX_NONE, POS_NONE};
     AMM_CUDA(cudaMemcpy(ws->ticket + 16, ident, sizeof(ident), cudaMemcpyHostToDevice));

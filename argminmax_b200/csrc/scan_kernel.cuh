@@ -931,15 +931,21 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   const uint64_t kstride_bytes = kstride_vecs * VEC;
   const uint64_t jstride = (uint64_t)blockDim.x * VEC;
 
-  // Dynamic tail (serialised scans only, see launch_packed): the last dyn_tiles full tiles of the
-  // array are not pre-assigned; a CTA that has finished its static share claims them one at a
-  // time from a counter in the workspace, so the CTAs finish together although they progress at
-  // very different rates (equal static shares finish 2.4x apart at 40 MB, 5 % apart at 4 GiB).
+  // Dynamic tail (see launch_packed): the last dyn_tiles full tiles of the array are not
+  // pre-assigned; a CTA that has finished its static share claims them one at a time from a
+  // counter in the workspace, so the CTAs finish together although they progress at very
+  // different rates (equal static shares finish 2.4x apart at 40 MB, 5 % apart at 4 GiB).
   // Claims are issued one tile ahead by thread 0 and broadcast through shared memory; claimed
   // tiles ascend per CTA and lie behind every static tile, so slot order stays address order.
+  // The counter is one of a ring of 64, picked by the call's sequence number, and is re-armed by
+  // the call's own last CTA.  Pipelined scans overlap, but call s + 64 cannot start claiming
+  // before call s has completed: a pipelined CTA cannot exit before the previous grid is complete
+  // (griddepcontrol.wait in the grid step), a grid only starts once every CTA of the one before
+  // it has started, and 63 whole grids of at least one CTA per SM do not fit on the GPU (32 CTAs
+  // per SM at most).
   __shared__ uint32_t s_claim[2];
   const uint32_t dyn_tiles = p.dyn_tiles;
-  uint32_t* const dyn_counter = p.ticket + 24;
+  uint32_t* const dyn_counter = p.ticket + 64 + (uint32_t)(p.seq & 63ull);
   uint32_t pending = 0;
   if (dyn_tiles != 0 && threadIdx.x == 0) pending = atomicAdd(dyn_counter, 1u);
   auto next_tile = [&](uint32_t i, const uint8_t*& q, uint32_t& t) -> bool {

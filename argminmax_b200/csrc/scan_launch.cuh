@@ -7,6 +7,7 @@
 #include "amm_internal.h"
 #include "scan_kernel.cuh"
 #include "windows_kernel.cuh"
+#include "ring_kernel.cuh"
 
 namespace amm {
 
@@ -23,6 +24,7 @@ static const VariantDesc kVariants[] __attribute__((unused)) = {
     {16, 8, 0, 2, "v16x8"},     // 3: 128-bit loads, 128 B/thread/tile, no software prefetch
     {16, 2, 1, 2, "v16x2_pf"},  // 4: small tiles
     {16, 4, 1, 0, "v16x4_pf_nohint"},  // 5: as 0 without the .L2::256B prefetch-size hint
+    {16, 8, 0, 0, "tma_ring_32k_x3"},  // 6: ring_kernel.cuh: 32 KiB tiles by TMA bulk copy, 3 stages, all tiles claimed
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 
@@ -79,10 +81,11 @@ static int launch_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, int v
   // How the tiles are handed out (profiles/r02_fixed_cost.md).  CTAs given equal shares finish
   // far apart -- the memory system serves them at very different rates (2.4x between the first
   // and the last CTA at 40 MB, +-2.6 % at 4 GiB) and the stragglers then stream alone, latency-
-  // bound.  So, for a scan that runs alone (not pipelined) and has at least two tiles per CTA:
-  //   DYNAMIC TAIL  the first tiles grid-stride, the last AMM_SCAN_DYN_PCT % claimed at run time.
-  // Otherwise (pipelined scans overlap their tail with the next scan anyway, and a claim counter
-  // cannot be shared by two grids in flight):
+  // bound.  So, with at least two tiles per CTA:
+  //   DYNAMIC TAIL  the first tiles grid-stride, the last AMM_SCAN_DYN_PCT % claimed at run time
+  //                 (8 % on HBM-sized inputs -- more costs a barrier per tile for nothing --
+  //                 30 % below 0.5 GiB);
+  // otherwise
   //   CONTIGUOUS    fewer than 64 tiles per CTA: equal ranges of whole rows (blockDim vectors);
   //   GRID-STRIDE   else: whole tiles b, b + G, ... (the +-1 tile imbalance is noise there).
   p.per_vecs = 0;
@@ -91,7 +94,11 @@ static int launch_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, int v
   p.rem_owner = 0;
   const bool big = p.n_bytes >= ((uint64_t)512 << 20);
   const int dyn_pct = ws->scan_dyn_pct >= 0 ? ws->scan_dyn_pct : (big ? 8 : 30);
-  const bool dynamic = dyn_pct > 0 && !p.pipelined && ws->scan_contig != 1 && full >= 2 * grid;
+  // (pipelined scans: only on HBM-sized inputs, +0.9 % at 4 GiB; below that the next scan's
+  // streaming already fills the gaps the stragglers leave and the claims only cost: 100 M u8
+  // 14.1 -> 15.4 us per call in a stream of calls)
+  const bool dynamic = dyn_pct > 0 && (!p.pipelined || (ws->scan_dyn_pipelined && big)) &&
+                       ws->scan_contig != 1 && full >= 2 * grid && grid >= (uint64_t)ws->sm_count;
   const bool contig = !dynamic && (ws->scan_contig < 0 ? tiles < 64 * grid : ws->scan_contig != 0);
   if (dynamic) {
     uint64_t dyn = full * (uint64_t)(dyn_pct > 90 ? 90 : dyn_pct) / 100;
@@ -155,6 +162,56 @@ static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int vari
       return launch_packed<P, VEC, U, PF, HINT, XCHG, true>(ws, p, dtype_slot, variant, stream);
   }
   return launch_packed<P, VEC, U, PF, HINT, XCHG, false>(ws, p, dtype_slot, variant, stream);
+}
+
+// HBM-sized inputs: the TMA-ring kernel (ring_kernel.cuh), every tile claimed at run time.
+template <class P, bool XCHG, bool PACKED>
+static int launch_ring_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStream_t stream) {
+  auto kernel = argminmax_ring_kernel<P, XCHG, PACKED>;
+  constexpr uint64_t VEC = 16;
+  const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
+  const uint64_t addr = (uint64_t)(uintptr_t)p.base;
+  uint64_t head = ((VEC - (addr % VEC)) % VEC) / sizeof(typename P::Elem);
+  if (head > p.n) head = p.n;
+  p.head_elems = head;
+  p.n_vec = (p.n - head) / vec_elems;
+  p.tail_start = head + p.n_vec * vec_elems;
+  const uint64_t full = p.n_vec / RING_TILE_VECS;
+  if ((full + 2) * (uint64_t)RING_U >= 0xFFFFFFFFull) return AMM_ERR_TOO_LARGE;  // 32-bit slot ids
+  p.n_full_tiles = (uint32_t)full;
+  p.rem_vecs = (uint32_t)(p.n_vec % RING_TILE_VECS);
+  p.rem_owner = 0;
+  p.per_vecs = 0;
+  p.dyn_tiles = 0;
+  p.dyn_koff = 0xFFFFFFFFu;
+  const size_t dyn = (size_t)RING_STAGES * RING_TILE_BYTES;
+  int& ready = ws->ring_ready[dtype_slot][(XCHG ? 1 : 0) + (PACKED ? 2 : 0)];
+  if (!ready) {
+    AMM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    ready = 1;
+  }
+  uint64_t grid = (uint64_t)ws->sm_count * (uint64_t)ws->ring_ctas_per_sm;
+  if (grid > (uint64_t)ws->max_grid) grid = (uint64_t)ws->max_grid;
+  if (grid > full + 1) grid = full + 1;
+  if (grid < 1) grid = 1;
+  AMM_CUDA(launch_scan(kernel, (unsigned)grid, (unsigned)RING_THREADS, stream, p, ws->pdl != 0, dyn));
+  ws->last_grid = (int)grid;
+  ws->last_threads = RING_THREADS;
+  ws->eff_threads = RING_THREADS;
+  ws->eff_ctas_per_sm = ws->ring_ctas_per_sm;
+  ws->eff_variant = kNumVariants - 1;
+  ws->launches += 1;
+  return AMM_OK;
+}
+
+template <class P, bool XCHG>
+static int launch_ring(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStream_t stream) {
+  if constexpr (sizeof(typename P::Key) == 4) {
+    const uint64_t vec_elems = 16 / sizeof(typename P::Elem);
+    if (ws->scan_packed && p.n / vec_elems < 0xFFFFFFFEull)
+      return launch_ring_packed<P, XCHG, true>(ws, p, dtype_slot, stream);
+  }
+  return launch_ring_packed<P, XCHG, false>(ws, p, dtype_slot, stream);
 }
 
 // Latency path for small inputs: one trip, see argminmax_direct_kernel.  Returns false when the
@@ -232,6 +289,15 @@ static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cuda
   // (128 KiB in flight per SM either way; with 2 CTAs per SM a 400 MB scan streams at 5.7 TB/s
   // instead of 6.9).
   const bool big = bytes >= ((uint64_t)512 << 20);
+  // Inputs of 2 GiB and more of 1/2/4-byte elements take the TMA-ring kernel: +0.8-1.2 % at 4 GiB
+  // (f32 7.39 -> 7.46 TB/s serialised, 7.43 -> 7.50 pipelined), level at 1 GiB; 8-byte dtypes keep
+  // the register path, whose 32-byte vectors halve their per-vector bookkeeping (ring: f64 -2.9 %).
+  // AMM_SCAN_RING=0: never, 1: for every streaming scan.
+  const bool ring = ws->variant == kNumVariants - 1 ||
+                    (ws->variant < 0 && (ws->scan_ring < 0 ? (bytes >= ((uint64_t)2 << 30) && sizeof(typename P::Elem) <= 4)
+                                                           : ws->scan_ring != 0));
+  if (ring) return p.world > 1 ? launch_ring<P, true>(ws, p, dtype_slot, stream)
+                               : launch_ring<P, false>(ws, p, dtype_slot, stream);
   ws->eff_variant = ws->variant >= 0 ? ws->variant : 1;
   ws->eff_threads = ws->threads > 0 ? ws->threads : 256;
   ws->eff_ctas_per_sm = ws->ctas_per_sm > 0 ? ws->ctas_per_sm : (big ? 8 : 4);

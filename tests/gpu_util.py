@@ -63,8 +63,8 @@ def _workspace_for(path: str):
     """'default': size-based choice; 'stream': always the streaming (tile) kernel, automatic
     tile partition; 'contig' / 'gridstride' / 'dynamic': the streaming kernel with the
     contiguous-range / static grid-stride / grid-stride + claimed-tail partition forced (the last
-    with tiny tiles so that small test arrays reach it); 'direct': the one-trip latency kernel
-    whenever the input fits."""
+    with tiny tiles so that small test arrays reach it); 'ring': the TMA-ring kernel of the
+    HBM-sized inputs for every size; 'direct': the one-trip latency kernel whenever the input fits."""
     import os
 
     from argminmax_b200 import Workspace
@@ -72,7 +72,8 @@ def _workspace_for(path: str):
         # the tile partition of the streaming kernel is a creation-time knob of the workspace
         knobs = {"contig": {"AMM_SCAN_CONTIG": "1"},
                  "gridstride": {"AMM_SCAN_CONTIG": "0", "AMM_SCAN_DYN_PCT": "0"},
-                 "dynamic": {"AMM_SCAN_CONTIG": "0", "AMM_SCAN_DYN_PCT": "50"}}.get(path, {})
+                 "dynamic": {"AMM_SCAN_CONTIG": "0", "AMM_SCAN_DYN_PCT": "50"},
+                 "ring": {"AMM_SCAN_RING": "1"}}.get(path, {})
         old = {k: os.environ.get(k) for k in knobs}
         os.environ.update(knobs)
         try:
@@ -86,7 +87,7 @@ def _workspace_for(path: str):
         if path == "dynamic":
             # 2 KiB tiles, one CTA per SM: the claimed tail is in play from ~600 KB upwards
             ws.set_tuning(64, 1, 4)
-        if path in ("stream", "contig", "gridstride", "dynamic"):
+        if path in ("stream", "contig", "gridstride", "dynamic", "ring"):
             ws.set_direct_threshold(0)
         elif path == "direct":
             ws.set_direct_threshold(1 << 62)
@@ -95,7 +96,7 @@ def _workspace_for(path: str):
 
 
 def assert_parity(arr: np.ndarray, mode: int, byte_offset: int = 0, what: str = "",
-                  paths=("default", "stream", "direct", "contig", "gridstride", "dynamic")):
+                  paths=("default", "stream", "direct", "contig", "gridstride", "dynamic", "ring")):
     ds, _keep = to_device(arr, byte_offset)
     exp = oracle.argminmax(arr, mode)
     got = None
