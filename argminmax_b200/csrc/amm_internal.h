@@ -69,6 +69,7 @@ struct amm_workspace {
   int win_staged;           // short windows take the TMA-staged kernel (AMM_WIN_STAGED=0: old path)
   int win_staged_max;       // ... for windows up to this many bytes (mean)
   int win_lane_bytes;       // ... with one lane per this many bytes of window (1..8 lanes)
+  int win_fixed;            // 32-bit-geometry instantiation for fixed windows that are not a multiple of 16 B (AMM_WIN_FIXED=0: off)
   int win_fast;             // geometry-free instantiation for aligned fixed windows (AMM_WIN_FAST=0: off)
   int win_chunks_per_sm;    // ... about this many chunks per SM in total
   int win_chunked;          // few 1-64 MiB windows are cut into chunks (AMM_WIN_CHUNKED=0: off)

@@ -337,6 +337,7 @@ static int workspace_init(amm_workspace* ws, int device) {
   ws->pdl = getenv("AMM_PDL") ? atoi(getenv("AMM_PDL")) : 1;
   ws->win_staged = getenv("AMM_WIN_STAGED") ? atoi(getenv("AMM_WIN_STAGED")) : 1;
   ws->win_fast = getenv("AMM_WIN_FAST") ? atoi(getenv("AMM_WIN_FAST")) : 1;
+  ws->win_fixed = getenv("AMM_WIN_FIXED") ? atoi(getenv("AMM_WIN_FIXED")) : 1;
   ws->win_chunks_per_sm = getenv("AMM_WIN_CHUNKS_PER_SM") ? atoi(getenv("AMM_WIN_CHUNKS_PER_SM")) : 16;
   if (ws->win_chunks_per_sm < 4 || ws->win_chunks_per_sm > 256) ws->win_chunks_per_sm = 16;
   ws->win_chunked = getenv("AMM_WIN_CHUNKED") ? atoi(getenv("AMM_WIN_CHUNKED")) : 1;

@@ -357,6 +357,28 @@ static int launch_windows_staged(amm_workspace* ws, const WindowParams& p, uint6
     rest.w_first = n_full;
     rest.n_windows = p.n_windows - n_full;
   }
+  // Fixed windows that are NOT a multiple of 16 bytes (16-byte aligned array): the leading full
+  // windows whose 16-byte-rounded end stays inside the array take the 32-bit-geometry kernel;
+  // the last one or two windows go to the general form.
+  if (p.offsets == nullptr && p.w_first == 0 && (p.window * ES) % 16 != 0 && p.window * ES >= 16 &&
+      ((uintptr_t)p.base % 16) == 0 && ws->win_fixed) {
+    uint64_t n_fix = p.n / p.window;  // full windows
+    const uint64_t n_bytes = p.n * ES;
+    while (n_fix > 0 && ((n_fix * p.window * ES + 15) & ~(uint64_t)15) > n_bytes) --n_fix;
+    if (n_fix > 0) {
+      WindowParams pf = p;
+      pf.n_windows = n_fix;
+      uint64_t stage = WPB * p.window * ES + 32;
+      stage = (stage + 127) / 128 * 128;
+      argminmax_windows_fixed_kernel<P, L, THREADS>
+          <<<grid_for(n_fix), THREADS, (size_t)(2 * stage), stream>>>(pf, (uint32_t)stage);
+      AMM_CUDA(cudaGetLastError());
+      ws->launches += 1;
+    }
+    if (n_fix >= p.n_windows) return AMM_OK;
+    rest.w_first = n_fix;
+    rest.n_windows = p.n_windows - n_fix;
+  }
   // stage = the bytes of one block of windows (+ alignment slack); ragged windows get 2x the
   // mean (what does not fit is read from global memory by the kernel)
   const uint64_t fixed_bytes = (p.window < p.n ? p.window : p.n) * ES;

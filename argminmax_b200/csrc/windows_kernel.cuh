@@ -645,6 +645,193 @@ __global__ void __launch_bounds__(THREADS)
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// SHORT FIXED windows whose size is NOT a multiple of 16 bytes (the usual down-sampling call: n
+// / bins is whatever it is), on a 16-byte aligned array.  The general staged kernel above handles
+// them, but its per-window geometry -- 64-bit window bounds, staged-range tests per access,
+// clamps for ragged / unordered / unstaged windows -- costs ~390 instructions per lane and made
+// u8 x 500 run at 2.6 TB/s where u8 x 512 (geometry-free) reaches 4.7.  Fixed windows need none
+// of that: every window of a block lies inside the block's stage at a byte offset that is a
+// 32-bit affine function of its position, so head / vector / tail counts are a handful of
+// 32-bit operations and every access is a shared-memory load.  Host contract (launch_windows_
+// staged): offsets == nullptr, base 16-byte aligned, all p.n_windows windows are FULL (p.window
+// elements) and the 16-byte-rounded end of the last one does not leave the array.
+// ---------------------------------------------------------------------------------------
+template <class Elem>
+__device__ __forceinline__ Elem lds_elem(uint32_t addr) {
+  uint32_t v;
+  if (sizeof(Elem) == 1) {
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (Elem)v;
+  } else if (sizeof(Elem) == 2) {
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (Elem)v;
+  } else if (sizeof(Elem) == 4) {
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return (Elem)v;
+  } else {
+    unsigned long long v8;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v8) : "r"(addr));
+    return (Elem)v8;
+  }
+}
+
+template <class P, int L, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+    argminmax_windows_fixed_kernel(const WindowParams p, const uint32_t stage_bytes) {
+  using Elem = typename P::Elem;
+  using Key = typename P::Key;
+  constexpr uint32_t ES = sizeof(Elem);
+  constexpr uint32_t VE = 16 / ES;
+  constexpr uint32_t WPB = THREADS / L;  // windows per block
+  extern __shared__ __align__(128) uint8_t dsm[];  // 2 stages x stage_bytes
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const uint32_t tid = threadIdx.x, lane = tid & 31;
+  const uint32_t wi = tid / L, l = tid % L;  // window in block, lane in window
+  const uint64_t n_blocks = (p.n_windows + WPB - 1) / WPB;
+  const bool out16 = (((uint64_t)(uintptr_t)p.out) & 15) == 0;
+  const uint32_t wbytes = (uint32_t)p.window * ES;
+
+  // block `blk`: its windows' bytes [first, first + cnt * wbytes), staged from floor16(first)
+  auto block_first_byte = [&](uint64_t blk) { return (p.w_first + blk * WPB) * p.window * ES; };
+  auto block_count = [&](uint64_t blk) {
+    const uint64_t wb = blk * WPB;
+    return (uint32_t)(wb + WPB < p.n_windows ? WPB : p.n_windows - wb);
+  };
+  auto issue = [&](uint64_t blk, uint32_t s) {
+    const uint64_t first = block_first_byte(blk);
+    const uint64_t lo = first & ~(uint64_t)15;
+    const uint64_t hi = (first + (uint64_t)block_count(blk) * wbytes + 15) & ~(uint64_t)15;
+    const uint32_t bytes = (uint32_t)(hi - lo);
+    mbar_arrive_expect_tx(&s_bar[s], bytes);
+    tma_bulk_g2s(dsm + (size_t)s * stage_bytes, p.base + lo, bytes, &s_bar[s]);
+  };
+
+  uint64_t blk = blockIdx.x;
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (blk < n_blocks) issue(blk, 0);
+  }
+  __syncthreads();
+  uint32_t it = 0;
+  for (; blk < n_blocks; blk += gridDim.x, ++it) {
+    const uint32_t s = it & 1;
+    // stage s^1 was released by the barrier that ended the previous iteration
+    if (tid == 0 && blk + gridDim.x < n_blocks) issue(blk + gridDim.x, s ^ 1);
+    const bool active = wi < block_count(blk);
+    // ---- this lane's window inside the stage (all 32-bit)
+    const uint32_t phase = (uint32_t)block_first_byte(blk) & 15u;
+    const uint32_t ob = phase + wi * wbytes;
+    uint32_t hb = (16u - (ob & 15u)) & 15u;  // head bytes up to the next 16-byte boundary
+    hb = hb < wbytes ? hb : wbytes;
+    const uint32_t hc = active ? hb / ES : 0;
+    const uint32_t nv = active ? (wbytes - hb) >> 4 : 0;
+    const uint32_t tc = active ? (wbytes - hb - (nv << 4)) / ES : 0;
+    const uint32_t s_head = smem_u32(dsm) + s * stage_bytes + ob;
+    const uint32_t s_vec = s_head + hb;
+    const uint32_t s_tail = s_vec + (nv << 4);
+    WinSrc src;  // only the staged-vector accessor is used
+    src.base = p.base;
+    src.a0 = src.a1 = 0;
+    src.stage_s = 0;
+    src.vec_staged = true;
+    src.vec_s = s_vec;
+    src.vec_g = nullptr;
+    mbar_wait(&s_bar[s], (it >> 1) & 1);
+
+    // ---- value-only fold of this lane's share: unit 0 = head, 1..nv = vectors, nv + 1 = tail
+    WinBest<Key> x;
+    x.clear();
+    for (uint32_t h = l; h < hc; h += L) {
+      Key k;
+      bool valid, is_nan;
+      P::classify(lds_elem<Elem>(s_head + h * ES), k, valid, is_nan);
+      x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, 0);
+    }
+    staged_fold_vectors<P, L, true>(src, nv, l, wi, x);
+    for (uint32_t q = l; q < tc; q += L) {
+      Key k;
+      bool valid, is_nan;
+      P::classify(lds_elem<Elem>(s_tail + q * ES), k, valid, is_nan);
+      x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, nv + 1);
+    }
+    // ---- reduce inside the lane group (lexicographic on (key, unit))
+#pragma unroll
+    for (int m = L / 2; m >= 1; m >>= 1) {
+      const Key okmin = __shfl_xor_sync(0xFFFFFFFFu, x.kmin, m);
+      const Key okmax = __shfl_xor_sync(0xFFFFFFFFu, x.kmax, m);
+      const uint32_t oumin = __shfl_xor_sync(0xFFFFFFFFu, x.umin, m);
+      const uint32_t oumax = __shfl_xor_sync(0xFFFFFFFFu, x.umax, m);
+      if (okmin < x.kmin || (okmin == x.kmin && oumin < x.umin)) {
+        x.kmin = okmin;
+        x.umin = oumin;
+      }
+      if (okmax > x.kmax || (okmax == x.kmax && oumax < x.umax)) {
+        x.kmax = okmax;
+        x.umax = oumax;
+      }
+      if (P::TRACK_NAN) {
+        const uint32_t ounan = __shfl_xor_sync(0xFFFFFFFFu, x.unan, m);
+        x.unan = ounan < x.unan ? ounan : x.unan;
+      }
+    }
+    // ---- resolve the winning units to element offsets inside the window: candidate c is
+    // handled by lane c % L of the group
+    auto locate = [&](uint32_t unit, int c, Key want) -> uint32_t {
+      auto is_hit = [&](Elem raw) {
+        Key k;
+        bool valid, is_nan;
+        P::classify(raw, k, valid, is_nan);
+        return c == 2 ? is_nan : (valid && k == want);
+      };
+      int found = -1;
+      if (unit >= 1 && unit <= nv) {
+        uint32_t w[4];
+        src.vec<true>(unit - 1, w);
+#pragma unroll
+        for (int e = (int)VE - 1; e >= 0; --e) found = is_hit(vec_elem<P, 4>(w, e)) ? e : found;
+        return found < 0 ? 0xFFFFFFFFu : hc + (unit - 1) * VE + (uint32_t)found;
+      }
+      const uint32_t addr = unit == 0 ? s_head : s_tail;
+      const uint32_t cnt = unit == 0 ? hc : tc;
+      for (int e = (int)cnt - 1; e >= 0; --e) found = is_hit(lds_elem<Elem>(addr + (uint32_t)e * ES)) ? e : found;
+      return found < 0 ? 0xFFFFFFFFu : (unit == 0 ? 0u : hc + nv * VE) + (uint32_t)found;
+    };
+    uint32_t res[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    constexpr int NC = P::TRACK_NAN ? 3 : 2;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const uint32_t unit = c == 0 ? x.umin : (c == 1 ? x.umax : x.unan);
+      uint32_t r = 0xFFFFFFFFu;
+      if (active && unit != 0xFFFFFFFFu && l == (uint32_t)(c % L)) r = locate(unit, c, c == 0 ? x.kmin : x.kmax);
+      if (L > 1) r = __shfl_sync(0xFFFFFFFFu, r, (int)(lane - l) + (c % L));
+      res[c] = r;
+    }
+    if (active && l == 0) {
+      const uint64_t wo = p.w_first + blk * WPB + wi;  // the array's window id
+      const uint64_t begin = wo * p.window;
+      uint64_t imin, imax;
+      if (p.mode == MODE_RETURN && res[2] != 0xFFFFFFFFu) {
+        imin = imax = begin + res[2];
+      } else if (res[0] == 0xFFFFFFFFu) {
+        imin = imax = begin;  // all NaN, ignore mode
+      } else {
+        imin = begin + res[0];
+        imax = begin + res[1];
+      }
+      if (out16) {
+        reinterpret_cast<ulonglong2*>(p.out)[wo] = make_ulonglong2(imin, imax);
+      } else {
+        p.out[2 * wo] = imin;
+        p.out[2 * wo + 1] = imax;
+      }
+    }
+    __syncthreads();  // everyone is done with stage s: it may be refilled
+  }
+}
+
 // Combine step of the chunked form: one warp per window folds the per-chunk answers.  Only
 // indices were kept per chunk; the candidates' values are re-read (two elements per chunk).
 // Chunks are visited in ascending order and merged lexicographically on (key, index), i.e. the

@@ -44,6 +44,41 @@ def test_fixed_windows(dt):
                 assert got == _expected(a, bounds, mode), (dt, window, mode)
 
 
+@pytest.mark.parametrize("dt", G.ALL_DTYPES)
+def test_fixed_windows_odd_sizes_on_an_aligned_array(dt):
+    """Fixed windows whose byte size is NOT a multiple of 16 on a 16-byte aligned array take the
+    32-bit-geometry staged kernel (argminmax_windows_fixed_kernel): every window starts at a
+    different phase of the 16-byte grid, so heads, tails and windows shorter than one vector all
+    occur; the last windows (rounded end outside the array, short last window) go to the general
+    kernel.  Few distinct values => ties inside and across units; NaN runs for floats."""
+    rng = np.random.default_rng(700 + G.ALL_DTYPES.index(dt))
+    es = np.dtype(G.NP[dt]).itemsize
+    n = 400_003
+    a = random_array(dt, n, rng)
+    dups = rng.integers(0, 4, n).astype(G.NP[dt])
+    a[::3] = dups[::3]                      # many ties
+    if dt in G.FLOAT_DTYPES:
+        a[rng.integers(0, n, 3000)] = np.nan
+        a[7000:7900] = np.nan               # whole windows of NaN
+    ds, _keep = to_device(a, byte_offset=0)
+    assert ds.data_ptr % 16 == 0
+    sizes = [w for w in (17, 33, 129, 500, 1001, 2047) if (w * es) % 16 != 0 and w * es >= 16]
+    sizes += [w for w in (3, 5, 9) if w * es >= 16 and (w * es) % 16 != 0]
+    assert sizes
+    for window in sizes:
+        for mode in modes_for(dt):
+            got = ds.argminmax_windows(window, mode).cpu().numpy()
+            exp = oracle.argminmax_windows(a, window, mode)
+            bad = np.nonzero((got != exp).any(axis=1))[0]
+            assert bad.size == 0, (dt, window, mode, int(bad[0]), got[bad[0]].tolist(), exp[bad[0]].tolist())
+    # the array ends exactly at a window end that is not 16-byte aligned, and at an aligned one
+    for n2 in (129 * 1000, 129 * 1024):
+        ds2, _k2 = to_device(a[:n2], byte_offset=0)
+        for mode in modes_for(dt):
+            got = ds2.argminmax_windows(129, mode).cpu().numpy()
+            assert (got == oracle.argminmax_windows(a[:n2], 129, mode)).all(), (dt, n2, mode)
+
+
 @pytest.mark.parametrize("dt", ["f32", "i16", "u8", "f64", "f16"])
 def test_ragged_windows_with_empty_and_duplicates(dt):
     import torch
