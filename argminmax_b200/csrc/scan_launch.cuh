@@ -194,6 +194,9 @@ static int launch_ring_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, 
   if (grid > (uint64_t)ws->max_grid) grid = (uint64_t)ws->max_grid;
   if (grid > full + 1) grid = full + 1;
   if (grid < 1) grid = 1;
+  // the claim-counter ring is safe for overlapping scans only when a grid has at least one CTA
+  // per SM (scan_kernel.cuh); smaller grids (the ring forced onto a small input) run serialised
+  if (grid < (uint64_t)ws->sm_count) p.pipelined = 0;
   AMM_CUDA(launch_scan(kernel, (unsigned)grid, (unsigned)RING_THREADS, stream, p, ws->pdl != 0, dyn));
   ws->last_grid = (int)grid;
   ws->last_threads = RING_THREADS;
@@ -298,9 +301,14 @@ static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cuda
                                                            : ws->scan_ring != 0));
   if (ring) return p.world > 1 ? launch_ring<P, true>(ws, p, dtype_slot, stream)
                                : launch_ring<P, false>(ws, p, dtype_slot, stream);
-  ws->eff_variant = ws->variant >= 0 ? ws->variant : 1;
+  // Pipelined scans below 128 MiB keep round 1's shape (128-bit loads, 2 CTAs per SM): the point of
+  // pipelining is that the NEXT scan's CTAs are resident and streaming while this one's tail runs,
+  // and 4 CTAs x 256 threads x 58-64 registers fill the SM (10 M f32 in a stream of calls: 6.6 us
+  // with 2 CTAs per SM, 7.3-7.5 with 4).
+  const bool small_pipelined = p.pipelined && bytes < ((uint64_t)128 << 20);
+  ws->eff_variant = ws->variant >= 0 ? ws->variant : (small_pipelined ? 0 : 1);
   ws->eff_threads = ws->threads > 0 ? ws->threads : 256;
-  ws->eff_ctas_per_sm = ws->ctas_per_sm > 0 ? ws->ctas_per_sm : (big ? 8 : 4);
+  ws->eff_ctas_per_sm = ws->ctas_per_sm > 0 ? ws->ctas_per_sm : (big ? 8 : (small_pipelined ? 2 : 4));
   if (p.world > 1) {
     // fused scan + peer exchange: instantiated for the two automatic shapes only
     if (ws->eff_variant != 0) ws->eff_variant = 1;

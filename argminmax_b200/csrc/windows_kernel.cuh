@@ -425,6 +425,78 @@ __device__ __forceinline__ void staged_fold_vectors(const WinSrc& src, uint32_t 
   }
 }
 
+// 8-byte dtypes in the staged kernels for FIXED windows: a 16-byte vector holds two elements, so
+// one `finish` + `consider` (~35 instructions with 64-bit keys) per vector is one per two
+// elements.  Here a unit is a PAIR of consecutive vectors (four elements): lane l folds pairs
+// l, l+L, ... (units p + 1); an odd last vector is its own unit (npairs + 1), taken by lane
+// npairs % L.  Two LDS.128 per unit at a 32-byte lane stride (2-way bank conflict: the kernels
+// are issue-bound, not shared-memory-bound).
+template <class P, int L>
+__device__ __forceinline__ void staged_fold_pairs(const WinSrc& src, uint32_t nv, uint32_t l,
+                                                  uint32_t wi, WinBest<typename P::Key>& x) {
+  using Key = typename P::Key;
+  static_assert(sizeof(typename P::Elem) == 8, "pairs of vectors are for 8-byte elements");
+  const uint32_t npairs = nv >> 1;
+  const uint32_t cnt = npairs > l ? (npairs - l + L - 1) / L : 0;
+  uint32_t kk = cnt ? wi % cnt : 0;
+  constexpr int UN = 2;
+  for (uint32_t k0 = 0; k0 < cnt; k0 += UN) {
+    uint32_t wv[UN][2][4];
+    uint32_t pp[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      pp[u] = l + kk * L;
+      if (k0 + u < cnt) {
+        src.vec<true>(2 * pp[u], wv[u][0]);
+        src.vec<true>(2 * pp[u] + 1, wv[u][1]);
+      }
+      ++kk;
+      kk = kk >= cnt ? 0 : kk;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (k0 + u < cnt) {
+        typename P::Acc acc;
+        P::init(acc, &wv[u][0][0]);
+        P::feed(acc, &wv[u][0][2]);
+        P::feed(acc, &wv[u][1][0]);
+        P::feed(acc, &wv[u][1][2]);
+        Key a, b;
+        bool valid, has_nan;
+        P::finish(acc, a, b, valid, has_nan);
+        x.template consider<P::TRACK_NAN>(a, b, valid, has_nan, pp[u] + 1);
+      }
+    }
+  }
+  if ((nv & 1u) && l == npairs % L) {  // the odd last vector
+    uint32_t w[4];
+    src.vec<true>(nv - 1, w);
+    typename P::Acc acc;
+    P::init(acc, &w[0]);
+    P::feed(acc, &w[2]);
+    Key a, b;
+    bool valid, has_nan;
+    P::finish(acc, a, b, valid, has_nan);
+    x.template consider<P::TRACK_NAN>(a, b, valid, has_nan, npairs + 1);
+  }
+}
+// element offset (from the first staged vector's first element) of the first hit inside pair-unit
+// `unit` (1-based, see staged_fold_pairs), or 0xFFFFFFFF
+template <class P, class Hit>
+__device__ __forceinline__ uint32_t staged_locate_pair(const WinSrc& src, uint32_t nv, uint32_t unit, Hit is_hit) {
+  const uint32_t npairs = nv >> 1;
+  const uint32_t v0 = unit <= npairs ? 2 * (unit - 1) : nv - 1;
+  const uint32_t nvec = unit <= npairs ? 2 : 1;
+  int found = -1;
+  for (int q = (int)nvec - 1; q >= 0; --q) {
+    uint32_t w[4];
+    src.vec<true>(v0 + (uint32_t)q, w);
+#pragma unroll
+    for (int e = 1; e >= 0; --e) found = is_hit(vec_elem<P, 4>(w, e)) ? q * 2 + e : found;
+  }
+  return found < 0 ? 0xFFFFFFFFu : v0 * 2 + (uint32_t)found;
+}
+
 // first element of unit `u` of window `g` that matches candidate `c` (0: key == kmin, 1: key ==
 // kmax, 2: NaN), or POS_NONE.  One thread, in registers for the 16-byte units.
 template <class P, bool FAST>
@@ -442,6 +514,10 @@ __device__ __forceinline__ uint64_t staged_locate(const WinSrc& src, const Windo
   uint64_t first;
   uint32_t count;
   int found = -1;
+  if (FAST && sizeof(Elem) == 8) {  // every unit is a pair of staged vectors (staged_fold_pairs)
+    const uint32_t off = staged_locate_pair<P>(src, (uint32_t)g.nv, unit, is_hit);
+    return off == 0xFFFFFFFFu ? POS_NONE : g.begin + (uint64_t)off;
+  }
   if (FAST) {  // every unit is a staged vector
     uint32_t w[4];
     src.vec<true>(unit - 1, w);
@@ -569,7 +645,11 @@ __global__ void __launch_bounds__(THREADS)
     WinBest<Key> x;
     x.clear();
     if constexpr (FAST) {
-      staged_fold_vectors<P, L, true>(src, (uint32_t)g.nv, l, wi, x);
+      if constexpr (sizeof(Elem) == 8) {
+        staged_fold_pairs<P, L>(src, (uint32_t)g.nv, l, wi, x);
+      } else {
+        staged_fold_vectors<P, L, true>(src, (uint32_t)g.nv, l, wi, x);
+      }
     } else {
       for (uint32_t h = l; h < g.hc; h += L) {  // unit 0: unaligned head
         Key k;
@@ -750,12 +830,18 @@ __global__ void __launch_bounds__(THREADS)
       P::classify(lds_elem<Elem>(s_head + h * ES), k, valid, is_nan);
       x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, 0);
     }
-    staged_fold_vectors<P, L, true>(src, nv, l, wi, x);
+    constexpr bool PAIRS = ES == 8;  // 8-byte dtypes: a vector unit is a pair of vectors
+    const uint32_t nvu = PAIRS ? (nv + 1) >> 1 : nv;  // vector units 1..nvu
+    if constexpr (PAIRS) {
+      staged_fold_pairs<P, L>(src, nv, l, wi, x);
+    } else {
+      staged_fold_vectors<P, L, true>(src, nv, l, wi, x);
+    }
     for (uint32_t q = l; q < tc; q += L) {
       Key k;
       bool valid, is_nan;
       P::classify(lds_elem<Elem>(s_tail + q * ES), k, valid, is_nan);
-      x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, nv + 1);
+      x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, nvu + 1);
     }
     // ---- reduce inside the lane group (lexicographic on (key, unit))
 #pragma unroll
@@ -787,12 +873,17 @@ __global__ void __launch_bounds__(THREADS)
         return c == 2 ? is_nan : (valid && k == want);
       };
       int found = -1;
-      if (unit >= 1 && unit <= nv) {
-        uint32_t w[4];
-        src.vec<true>(unit - 1, w);
+      if (unit >= 1 && unit <= nvu) {
+        if constexpr (PAIRS) {
+          const uint32_t off = staged_locate_pair<P>(src, nv, unit, is_hit);
+          return off == 0xFFFFFFFFu ? off : hc + off;
+        } else {
+          uint32_t w[4];
+          src.vec<true>(unit - 1, w);
 #pragma unroll
-        for (int e = (int)VE - 1; e >= 0; --e) found = is_hit(vec_elem<P, 4>(w, e)) ? e : found;
-        return found < 0 ? 0xFFFFFFFFu : hc + (unit - 1) * VE + (uint32_t)found;
+          for (int e = (int)VE - 1; e >= 0; --e) found = is_hit(vec_elem<P, 4>(w, e)) ? e : found;
+          return found < 0 ? 0xFFFFFFFFu : hc + (unit - 1) * VE + (uint32_t)found;
+        }
       }
       const uint32_t addr = unit == 0 ? s_head : s_tail;
       const uint32_t cnt = unit == 0 ? hc : tc;

@@ -331,14 +331,24 @@ def run_reference(args) -> int:
 
 
 # ----------------------------------------------------------------- helper probes
-def events_us(torch, fn, iters: int) -> float:
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        fn(i)
-    e1.record()
-    e1.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3
+def events_us(torch, fn, iters: int, batch: int = 0) -> float:
+    """Mean device time per call of `fn` over `iters` back-to-back calls, CUDA events on the current
+    stream.  `batch` > 0: the calls go out in batches of that many with a sync in between, so that
+    the host never runs hundreds of launches ahead of the device (with 200 scans queued at once
+    the same serialised 4 GiB scans measure 0.593 ms instead of 0.575)."""
+    total_ms, done = 0.0, 0
+    step = batch if batch > 0 else iters
+    while done < iters:
+        m = min(step, iters - done)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(done, done + m):
+            fn(i)
+        e1.record()
+        e1.synchronize()
+        total_ms += e0.elapsed_time(e1)
+        done += m
+    return total_ms / iters * 1e3
 
 
 def serialised_probes(torch, amm, ws, data, stream) -> dict:
@@ -360,7 +370,7 @@ def serialised_probes(torch, amm, ws, data, stream) -> dict:
             s.launch(amm.IGNORE_NAN)
         slices[0].wait(amm.IGNORE_NAN)
         iters = 200 if nbytes <= (64 << 20) else 60
-        us = events_us(torch, lambda i: slices[i % segs].launch(amm.IGNORE_NAN), iters)
+        us = events_us(torch, lambda i: slices[i % segs].launch(amm.IGNORE_NAN), iters, batch=50)
         slices[0].wait(amm.IGNORE_NAN)
         out[key] = {"us": round(us, 2), "gbs": round(nbytes / us / 1e3, 1), "segments": segs,
                     "cold_l2": segs * stride >= (256 << 20)}
@@ -462,7 +472,7 @@ def emit(line: dict) -> None:
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--elems", type=int, default=N_ELEMS, help="elements per GPU (default 2^30)")
@@ -616,7 +626,7 @@ def main() -> int:
     xws.set_pipelined(False)
     for _ in range(2):
         shard.launch(amm.IGNORE_NAN)
-    kernel_ms = events_us(torch, lambda i: shard.launch(amm.IGNORE_NAN), args.steps) / 1e3
+    kernel_ms = events_us(torch, lambda i: shard.launch(amm.IGNORE_NAN), args.steps, batch=20) / 1e3
     shard.wait(amm.IGNORE_NAN)
     peak, peak_src = measured_peak()
     achieved = nbytes / kernel_ms / 1e6
@@ -631,6 +641,10 @@ def main() -> int:
 
     extras = {}
     if not args.no_extras:
+        # the probes below are single calls: let the GPU settle after the streaming loops above (a
+        # B200 that has just streamed for a while answers short kernels ~1.7 us slower for some
+        # hundred ms: tools/exp/latency_after_load.py)
+        time.sleep(0.5)
         # ---- strong scaling: 2^30 elements IN TOTAL over the N GPUs (each scans 2^30/N of its
         #      buffer), serialised collective calls; N=1 reference = kernel_ms above
         if distributed:
