@@ -7,9 +7,9 @@
 //     workspace's claim counter -- every tile of the array, not just a tail: the claim costs the
 //     consumers nothing -- and fetches each with ONE cp.async.bulk (global -> shared, UBLKCP,
 //     completion on an mbarrier) into a ring of 3 stages; the tile id travels with the stage;
-//   * 256 CONSUMER threads wait for a stage, pull their 8 x 16 bytes out of shared memory
-//     (conflict-free: lane i reads bytes [16 i, 16 i + 16) of every 4 KiB row), fold them, and
-//     hand the stage back (mbarrier with 256 arrivals).
+//   * 256 CONSUMER threads wait for a stage, pull their 128 bytes out of shared memory (8 x 16
+//     bytes, lane i reads bytes [16 i, 16 i + 16) of every 4 KiB row; 8-byte dtypes 4 x 32
+//     bytes), fold them, and hand the stage back (mbarrier with 256 arrivals).
 //
 // Bytes in flight are bounded by shared memory (2 CTAs x 96 KiB per SM) instead of registers
 // (4 CTAs x 256 threads x 128 B = 128 KiB), the memory system sees 32 KiB sequential requests,
@@ -17,9 +17,9 @@
 // (tools/exp/tma_ring.cu, profiles/r02_tma_ring.md): 7.54 TB/s against 7.42-7.45 for the register
 // ping-pong on the same 4 GiB -- but only WITH the producer-side claims (a static ring: 7.0).
 // In the product (same file): f32 x 2^30 serialised 7.39 -> 7.46 TB/s, pipelined 7.43 -> 7.50.
-// Used for inputs of at least 2 GiB of 1/2/4-byte elements (launch_variant); smaller inputs keep
-// the register path (level at 1 GiB, lower fixed cost below), and so do 8-byte dtypes (16-byte
-// units double their per-unit bookkeeping: f64 -2.9 %).
+// Used for inputs of at least 2 GiB (launch_variant); smaller inputs keep the register path
+// (level at 1 GiB, lower fixed cost below).  With 16-byte vectors the 8-byte dtypes lost against
+// the register path's 32-byte vectors (f64 -2.9 %): they get 32-byte vectors here too (RingGeom).
 #pragma once
 #include "scan_kernel.cuh"
 #include "windows_kernel.cuh"  // mbarrier / bulk-copy helpers
@@ -29,15 +29,24 @@ namespace amm {
 constexpr int RING_CONSUMERS = 256;
 constexpr int RING_THREADS = RING_CONSUMERS + 32;  // + the producer warp
 constexpr int RING_STAGES = 3;
-constexpr int RING_U = 8;                                   // 16-byte vectors per consumer per tile
-constexpr uint32_t RING_TILE_VECS = RING_CONSUMERS * RING_U;  // 2048
-constexpr uint32_t RING_TILE_BYTES = RING_TILE_VECS * 16;     // 32 KiB
+constexpr uint32_t RING_TILE_BYTES = 32768;  // 32 KiB
 constexpr uint32_t RING_END = 0xFFFFFFFFu;
+// A consumer's vector is 16 bytes (one LDS.128; rows of 4 KiB, conflict-free) for 1/2/4-byte
+// elements and 32 bytes (two LDS.128 at a 32-byte lane stride: 2-way bank conflict, far from the
+// shared-memory limit) for 8-byte elements, whose per-vector bookkeeping -- 64-bit keys -- is
+// then paid per four elements instead of per two.
+template <class P>
+struct RingGeom {
+  static constexpr int VEC = sizeof(typename P::Elem) == 8 ? 32 : 16;
+  static constexpr int U = RING_TILE_BYTES / (RING_CONSUMERS * VEC);  // vectors per consumer per tile: 8 / 4
+  static constexpr uint32_t TILE_VECS = RING_CONSUMERS * U;           // 2048 / 1024
+};
 
 template <class P, bool XCHG, bool PACKED>
 __global__ void __launch_bounds__(RING_THREADS) argminmax_ring_kernel(const ScanParams p) {
   using Key = typename P::Key;
-  constexpr int VEC = 16, NW = 4, U = RING_U;
+  constexpr int VEC = RingGeom<P>::VEC, NW = VEC / 4, U = RingGeom<P>::U;
+  constexpr uint32_t RING_TILE_VECS = RingGeom<P>::TILE_VECS;
   constexpr uint32_t VEC_ELEMS = VEC / sizeof(typename P::Elem);
   static_assert(!PACKED || sizeof(Key) == 4, "packed candidates need 32-bit keys");
   extern __shared__ __align__(128) uint8_t ring[];  // RING_STAGES x RING_TILE_BYTES
@@ -121,9 +130,11 @@ __global__ void __launch_bounds__(RING_THREADS) argminmax_ring_kernel(const Scan
       const uint32_t sb = my + s * RING_TILE_BYTES;
 #pragma unroll
       for (int j = 0; j < U; ++j)
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                     : "=r"(a[j][0]), "=r"(a[j][1]), "=r"(a[j][2]), "=r"(a[j][3])
-                     : "r"(sb + j * (RING_CONSUMERS * VEC)));
+#pragma unroll
+        for (int h = 0; h < NW; h += 4)
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(a[j][h]), "=r"(a[j][h + 1]), "=r"(a[j][h + 2]), "=r"(a[j][h + 3])
+                       : "r"(sb + j * (RING_CONSUMERS * VEC) + h * 4));
       mbar_arrive(&s_empty[s]);  // the registers hold the data: the stage may be refilled
       fold_tile<P, NW, U>(a, t, run);
 #ifdef AMM_PHASE_STAMPS

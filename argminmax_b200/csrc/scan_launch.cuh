@@ -168,7 +168,8 @@ static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int vari
 template <class P, bool XCHG, bool PACKED>
 static int launch_ring_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStream_t stream) {
   auto kernel = argminmax_ring_kernel<P, XCHG, PACKED>;
-  constexpr uint64_t VEC = 16;
+  constexpr uint64_t VEC = RingGeom<P>::VEC;
+  constexpr uint64_t TILE_VECS = RingGeom<P>::TILE_VECS;
   const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
   const uint64_t addr = (uint64_t)(uintptr_t)p.base;
   uint64_t head = ((VEC - (addr % VEC)) % VEC) / sizeof(typename P::Elem);
@@ -176,10 +177,10 @@ static int launch_ring_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, 
   p.head_elems = head;
   p.n_vec = (p.n - head) / vec_elems;
   p.tail_start = head + p.n_vec * vec_elems;
-  const uint64_t full = p.n_vec / RING_TILE_VECS;
-  if ((full + 2) * (uint64_t)RING_U >= 0xFFFFFFFFull) return AMM_ERR_TOO_LARGE;  // 32-bit slot ids
+  const uint64_t full = p.n_vec / TILE_VECS;
+  if ((full + 2) * (uint64_t)RingGeom<P>::U >= 0xFFFFFFFFull) return AMM_ERR_TOO_LARGE;  // 32-bit slot ids
   p.n_full_tiles = (uint32_t)full;
-  p.rem_vecs = (uint32_t)(p.n_vec % RING_TILE_VECS);
+  p.rem_vecs = (uint32_t)(p.n_vec % TILE_VECS);
   p.rem_owner = 0;
   p.per_vecs = 0;
   p.dyn_tiles = 0;
@@ -210,7 +211,7 @@ static int launch_ring_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, 
 template <class P, bool XCHG>
 static int launch_ring(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStream_t stream) {
   if constexpr (sizeof(typename P::Key) == 4) {
-    const uint64_t vec_elems = 16 / sizeof(typename P::Elem);
+    const uint64_t vec_elems = RingGeom<P>::VEC / sizeof(typename P::Elem);
     if (ws->scan_packed && p.n / vec_elems < 0xFFFFFFFEull)
       return launch_ring_packed<P, XCHG, true>(ws, p, dtype_slot, stream);
   }
@@ -292,13 +293,11 @@ static int launch_variant(amm_workspace* ws, ScanParams& p, int dtype_slot, cuda
   // (128 KiB in flight per SM either way; with 2 CTAs per SM a 400 MB scan streams at 5.7 TB/s
   // instead of 6.9).
   const bool big = bytes >= ((uint64_t)512 << 20);
-  // Inputs of 2 GiB and more of 1/2/4-byte elements take the TMA-ring kernel: +0.8-1.2 % at 4 GiB
-  // (f32 7.39 -> 7.46 TB/s serialised, 7.43 -> 7.50 pipelined), level at 1 GiB; 8-byte dtypes keep
-  // the register path, whose 32-byte vectors halve their per-vector bookkeeping (ring: f64 -2.9 %).
+  // Inputs of 2 GiB and more take the TMA-ring kernel: +0.8-1.2 % at 4 GiB (f32 7.39 -> 7.46 TB/s
+  // serialised, 7.43 -> 7.50 pipelined), +2 % at 64 GiB, level at 1 GiB.
   // AMM_SCAN_RING=0: never, 1: for every streaming scan.
   const bool ring = ws->variant == kNumVariants - 1 ||
-                    (ws->variant < 0 && (ws->scan_ring < 0 ? (bytes >= ((uint64_t)2 << 30) && sizeof(typename P::Elem) <= 4)
-                                                           : ws->scan_ring != 0));
+                    (ws->variant < 0 && (ws->scan_ring < 0 ? bytes >= ((uint64_t)2 << 30) : ws->scan_ring != 0));
   if (ring) return p.world > 1 ? launch_ring<P, true>(ws, p, dtype_slot, stream)
                                : launch_ring<P, false>(ws, p, dtype_slot, stream);
   // Pipelined scans below 128 MiB keep round 1's shape (128-bit loads, 2 CTAs per SM): the point of
