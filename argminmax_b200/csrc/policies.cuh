@@ -62,6 +62,7 @@ struct PolInt32 {
   using Key = int32_t;
   static constexpr int WPI = 1;  // 32-bit words consumed per feed()
   static constexpr bool TRACK_NAN = false;
+  static constexpr bool SIMD_EQ = false;  // no packed equality compare for this element width
   struct Acc {
     uint32_t mn, mx;
   };
@@ -99,6 +100,9 @@ struct PolInt16 {
   using Key = int32_t;
   static constexpr int WPI = 1;
   static constexpr bool TRACK_NAN = false;
+  // no packed equality locate: with 8 trivially-keyed elements per vector the scalar compare chain
+  // is shorter than __vcmpeq2 + find-first-set per word (measured: i16 windows 8-13 % slower with it)
+  static constexpr bool SIMD_EQ = false;
   struct Acc {
     uint32_t mn, mx;  // two packed 16-bit lanes each
   };
@@ -141,6 +145,16 @@ struct PolInt8 {
   using Key = int32_t;
   static constexpr int WPI = 1;
   static constexpr bool TRACK_NAN = false;
+  // first element of a 32-bit word whose raw bits equal the (bijective) key's: packed compare
+  // (__vcmpeq4) + find-first-set instead of an extract + classify + compare per element (16 per
+  // vector here; u8 / f16 windows of 16-1000 elements +4-23 %)
+  static constexpr bool SIMD_EQ = true;
+  static constexpr int PER_WORD = 4;
+  static __device__ __forceinline__ uint32_t raw_bcast(Key k) { return (uint32_t)(uint8_t)k * 0x01010101u; }
+  static __device__ __forceinline__ int first_eq(uint32_t w, uint32_t bc) {
+    const uint32_t m = __vcmpeq4(w, bc);
+    return m ? (__ffs(m) - 1) >> 3 : -1;
+  }
   struct Acc {
     uint32_t mnA, mnB, mxA, mxB;  // A: odd bytes, B: even bytes (both in lane-high position)
   };
@@ -186,6 +200,7 @@ struct PolInt64 {
   using Key = int64_t;
   static constexpr int WPI = 2;
   static constexpr bool TRACK_NAN = false;
+  static constexpr bool SIMD_EQ = false;  // no packed equality compare for this element width
   struct Acc {
     uint64_t mn, mx;
   };
@@ -227,6 +242,7 @@ struct PolF32 {
   using Key = int32_t;
   static constexpr int WPI = 1;
   static constexpr bool TRACK_NAN = (MODE == MODE_RETURN);
+  static constexpr bool SIMD_EQ = false;  // no packed equality compare for this element width
   struct Acc {
     float mn, mx;
   };
@@ -275,6 +291,17 @@ struct PolF16 {
   using Key = int32_t;
   static constexpr int WPI = 1;
   static constexpr bool TRACK_NAN = (MODE == MODE_RETURN);
+  static constexpr bool SIMD_EQ = true;  // see PolInt8; the ord transform is its own inverse
+  static constexpr int PER_WORD = 2;
+  static __device__ __forceinline__ uint32_t raw_bcast(Key k) {
+    const int16_t s = (int16_t)k;
+    const uint32_t r = (uint32_t)(uint16_t)(s ^ ((int16_t)(s >> 15) & 0x7FFF));
+    return r | (r << 16);
+  }
+  static __device__ __forceinline__ int first_eq(uint32_t w, uint32_t bc) {
+    const uint32_t m = __vcmpeq2(w, bc);
+    return m ? (__ffs(m) - 1) >> 4 : -1;
+  }
   struct Acc {
     __half2 mn, mx;
   };
@@ -333,6 +360,7 @@ struct PolF64<MODE_IGNORE> {
   using Key = int64_t;
   static constexpr int WPI = 2;
   static constexpr bool TRACK_NAN = false;
+  static constexpr bool SIMD_EQ = false;  // no packed equality compare for this element width
   struct Acc {
     double mn, mx;
   };
@@ -371,6 +399,7 @@ struct PolF64<MODE_RETURN> {
   using Key = int64_t;
   static constexpr int WPI = 2;
   static constexpr bool TRACK_NAN = true;
+  static constexpr bool SIMD_EQ = false;  // no packed equality compare for this element width
   struct Acc {
     double mn, mx;
     bool nan;
@@ -401,5 +430,19 @@ struct PolF64<MODE_RETURN> {
     k = key_f64(raw);
   }
 };
+
+// index of the first element of a 16-byte vector whose key equals `want` (a key of a non-NaN
+// element), or -1; policies with SIMD_EQ only
+template <class P>
+__device__ __forceinline__ int vec_first_eq(const uint32_t (&w)[4], typename P::Key want) {
+  const uint32_t bc = P::raw_bcast(want);
+  int found = -1;
+#pragma unroll
+  for (int i = 3; i >= 0; --i) {
+    const int f = P::first_eq(w[i], bc);
+    found = f >= 0 ? i * P::PER_WORD + f : found;
+  }
+  return found;
+}
 
 }  // namespace amm

@@ -747,14 +747,28 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
     const bool is_min = (u == umin), is_max = (u == umax), is_nan = P::TRACK_NAN && (u == unan);
     if (is_min || is_max || is_nan) {
       int emin = VE, emax = VE, enan = VE;
+      if constexpr (P::SIMD_EQ) {  // 8- / 16-bit elements: packed equality compare + find-first-set
+        if (is_min) emin = vec_first_eq<P>(w[u], bkmin);
+        if (is_max) emax = vec_first_eq<P>(w[u], bkmax);
+        if (is_nan) {
 #pragma unroll
-      for (int e = VE - 1; e >= 0; --e) {
-        Key k;
-        bool valid, nan;
-        P::classify(vec_elem<P, NW>(w[u], e), k, valid, nan);
-        emin = (valid && k == bkmin) ? e : emin;
-        emax = (valid && k == bkmax) ? e : emax;
-        if (P::TRACK_NAN) enan = nan ? e : enan;
+          for (int e = VE - 1; e >= 0; --e) {
+            Key k;
+            bool valid, nan;
+            P::classify(vec_elem<P, NW>(w[u], e), k, valid, nan);
+            enan = nan ? e : enan;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int e = VE - 1; e >= 0; --e) {
+          Key k;
+          bool valid, nan;
+          P::classify(vec_elem<P, NW>(w[u], e), k, valid, nan);
+          emin = (valid && k == bkmin) ? e : emin;
+          emax = (valid && k == bkmax) ? e : emax;
+          if (P::TRACK_NAN) enan = nan ? e : enan;
+        }
       }
       const uint64_t i0 = p.head_elems + (v0 + (uint64_t)u * blockDim.x) * VE;
       if (is_min) {

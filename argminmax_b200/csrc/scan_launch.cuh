@@ -354,9 +354,17 @@ static int launch_windows_staged(amm_workspace* ws, const WindowParams& p, uint6
     if (n_full > 0) {
       WindowParams pf = p;
       pf.n_windows = n_full;
-      const uint64_t stage = WPB * p.window * ES;  // <= 128 lanes x 128 B = 16 KiB by the dispatch rule
+      // tiny windows: several passes per block so that a block (one bulk copy, one barrier) is
+      // ~8 KiB or more; <= 128 lanes x 128 B = 16 KiB per stage by the dispatch rule
+      const uint64_t pass_bytes = WPB * p.window * ES;
+      uint64_t kwin = pass_bytes >= 8192 ? 1 : 8192 / pass_bytes;
+      if (kwin > 8) kwin = 8;
+      const uint64_t stage = pass_bytes * kwin;
+      const uint64_t n_blocks = (n_full + WPB * kwin - 1) / (WPB * kwin);
+      uint64_t grid = (uint64_t)ws->sm_count * 6;
+      grid = n_blocks < grid ? n_blocks : grid;
       argminmax_windows_staged_kernel<P, L, THREADS, true>
-          <<<grid_for(n_full), THREADS, (size_t)(2 * stage), stream>>>(pf, (uint32_t)stage);
+          <<<(unsigned)(grid < 1 ? 1 : grid), THREADS, (size_t)(2 * stage), stream>>>(pf, (uint32_t)stage, (uint32_t)kwin);
       AMM_CUDA(cudaGetLastError());
       ws->launches += 1;
     }
@@ -394,7 +402,7 @@ static int launch_windows_staged(amm_workspace* ws, const WindowParams& p, uint6
   if (stage < 1024) stage = 1024;
   if (stage > 20480) stage = 20480;  // 2 stages + static smem stay below the 48 KB default limit
   argminmax_windows_staged_kernel<P, L, THREADS>
-      <<<grid_for(rest.n_windows), THREADS, (size_t)(2 * stage), stream>>>(rest, (uint32_t)stage);
+      <<<grid_for(rest.n_windows), THREADS, (size_t)(2 * stage), stream>>>(rest, (uint32_t)stage, 1u);
   AMM_CUDA(cudaGetLastError());
   ws->launches += 1;
   return AMM_OK;

@@ -521,6 +521,12 @@ __device__ __forceinline__ uint64_t staged_locate(const WinSrc& src, const Windo
   if (FAST) {  // every unit is a staged vector
     uint32_t w[4];
     src.vec<true>(unit - 1, w);
+    if constexpr (P::SIMD_EQ) {
+      if (c != 2) {
+        found = vec_first_eq<P>(w, want);
+        return found < 0 ? POS_NONE : g.begin + (uint64_t)(unit - 1) * VE + (uint64_t)found;
+      }
+    }
 #pragma unroll
     for (int e = VE - 1; e >= 0; --e) found = is_hit(vec_elem<P, 4>(w, e)) ? e : found;
     return found < 0 ? POS_NONE : g.begin + (uint64_t)(unit - 1) * VE + (uint64_t)found;
@@ -546,24 +552,28 @@ __device__ __forceinline__ uint64_t staged_locate(const WinSrc& src, const Windo
 // geometry (head / tail, staged-range tests, clamps) disappears.
 template <class P, int L, int THREADS, bool FAST = false>
 __global__ void __launch_bounds__(THREADS)
-    argminmax_windows_staged_kernel(const WindowParams p, const uint32_t stage_bytes) {
+    argminmax_windows_staged_kernel(const WindowParams p, const uint32_t stage_bytes, const uint32_t kwin) {
   using Elem = typename P::Elem;
   using Key = typename P::Key;
-  constexpr uint32_t WPB = THREADS / L;  // windows per block
+  constexpr uint32_t WPB = THREADS / L;  // windows per pass of the CTA
+  // A block is kwin passes: with tiny windows (16-64 bytes) one pass is 2-8 KiB, too little per
+  // bulk copy and per barrier to keep the SM's memory pipeline full; the host picks kwin so that a
+  // block is ~8 KiB or more (FAST form only, else 1).
+  const uint32_t WPBK = WPB * kwin;
   extern __shared__ __align__(128) uint8_t dsm[];  // 2 stages x stage_bytes
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ uint64_t s_range[2][2];  // staged byte range [a0, a1) of each stage
   const uint32_t tid = threadIdx.x, lane = tid & 31;
-  const uint32_t wi = tid / L, l = tid % L;  // window in block, lane in window
-  const uint64_t n_blocks = (p.n_windows + WPB - 1) / WPB;
+  const uint32_t wi = tid / L, l = tid % L;  // window in pass, lane in window
+  const uint64_t n_blocks = (p.n_windows + WPBK - 1) / WPBK;
   const bool out16 = (((uint64_t)(uintptr_t)p.out) & 15) == 0;
 
   // thread 0: staged byte range of block `blk`, published in s_range[s], and the copy itself
   const uint32_t wvec = FAST ? (uint32_t)(p.window / WindowGeom<P>::VE) : 0;  // vectors per window
   auto issue = [&](uint64_t blk, uint32_t s) {
     if (FAST) {
-      const uint64_t wb = blk * WPB;
-      const uint64_t cnt = wb + WPB < p.n_windows ? WPB : p.n_windows - wb;
+      const uint64_t wb = blk * WPBK;
+      const uint64_t cnt = wb + WPBK < p.n_windows ? WPBK : p.n_windows - wb;
       const uint32_t bytes = (uint32_t)(cnt * wvec * 16);
       mbar_arrive_expect_tx(&s_bar[s], bytes);
       tma_bulk_g2s(dsm + (size_t)s * stage_bytes,
@@ -576,8 +586,8 @@ __global__ void __launch_bounds__(THREADS)
     const uint64_t in_lo = (16 - (abase & 15)) & 15;
     const uint64_t hi_abs = (abase + n_bytes) & ~(uint64_t)15;
     const uint64_t in_hi = hi_abs > abase ? hi_abs - abase : 0;  // may be < in_lo (tiny arrays)
-    const uint64_t wb = blk * WPB;
-    const uint64_t we = (wb + WPB < p.n_windows ? wb + WPB : p.n_windows) - 1;  // last window
+    const uint64_t wb = blk * WPBK;
+    const uint64_t we = (wb + WPBK < p.n_windows ? wb + WPBK : p.n_windows) - 1;  // last window
     uint64_t b0, e0, b1, e1;
     window_bounds<P>(p, wb, b0, e0);
     window_bounds<P>(p, we, b1, e1);
@@ -614,7 +624,9 @@ __global__ void __launch_bounds__(THREADS)
     const uint32_t s = it & 1;
     // stage s^1 was released by the barrier that ended the previous iteration
     if (tid == 0 && blk + gridDim.x < n_blocks) issue(blk + gridDim.x, s ^ 1);
-    const uint64_t w = blk * WPB + wi;
+    for (uint32_t kp = 0; kp < kwin; ++kp) {
+    const uint32_t wk = kp * WPB + wi;  // this lane group's window inside the block
+    const uint64_t w = blk * WPBK + wk;
     const bool active = w < p.n_windows;
     WinSrc src;
     src.base = p.base;
@@ -623,7 +635,7 @@ __global__ void __launch_bounds__(THREADS)
       if constexpr (FAST) {
         src.a0 = src.a1 = 0;
         src.vec_staged = true;
-        src.vec_s = src.stage_s + wi * wvec * 16u;
+        src.vec_s = src.stage_s + wk * wvec * 16u;
         src.vec_g = nullptr;
         return WindowGeom<P>((p.w_first + w) * p.window, active ? wvec : 0u);
       } else {
@@ -639,7 +651,7 @@ __global__ void __launch_bounds__(THREADS)
         return gg;
       }
     }();
-    mbar_wait(&s_bar[s], (it >> 1) & 1);
+    if (kp == 0) mbar_wait(&s_bar[s], (it >> 1) & 1);
 
     // ---- value-only fold of this lane's share of the window
     WinBest<Key> x;
@@ -721,6 +733,7 @@ __global__ void __launch_bounds__(THREADS)
         p.out[2 * wo + 1] = imax;
       }
     }
+    }  // passes of the block
     __syncthreads();  // everyone is done with stage s: it may be refilled
   }
 }
@@ -880,8 +893,17 @@ __global__ void __launch_bounds__(THREADS)
         } else {
           uint32_t w[4];
           src.vec<true>(unit - 1, w);
+          bool done = false;
+          if constexpr (P::SIMD_EQ) {
+            if (c != 2) {
+              found = vec_first_eq<P>(w, want);
+              done = true;
+            }
+          }
+          if (!done) {
 #pragma unroll
-          for (int e = (int)VE - 1; e >= 0; --e) found = is_hit(vec_elem<P, 4>(w, e)) ? e : found;
+            for (int e = (int)VE - 1; e >= 0; --e) found = is_hit(vec_elem<P, 4>(w, e)) ? e : found;
+          }
           return found < 0 ? 0xFFFFFFFFu : hc + (unit - 1) * VE + (uint32_t)found;
         }
       }

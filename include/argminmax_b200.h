@@ -289,8 +289,10 @@ int amm_version(void);                /* AMM_VERSION_MAJOR * 100 + AMM_VERSION_M
 
 /* Scan geometry knobs (benchmarks / tuning only).  By default the library picks the geometry
    per call from the input size.  threads: CTA size (multiple of 32, 64..512); ctas_per_sm:
-   persistent CTAs per SM; variant: load shape, see amm_variant_name().  threads /
-   ctas_per_sm <= 0 and variant < 0 select "automatic" for that knob.  get_tuning reports what
+   persistent CTAs per SM; variant: load shape, see amm_variant_name() (the last one is the TMA-ring
+   kernel, which has its own fixed geometry).  threads / ctas_per_sm <= 0 and variant < 0 select
+   "automatic" for that knob: 256-bit loads, 256 threads, 4 CTAs per SM and a claimed tail of the
+   tile sequence; the TMA ring from 2 GiB.  get_tuning reports what
    the most recent streaming launch actually used. */
 int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, int variant);
 /* Pipelined mode for back-to-back scans on one stream (many resident arrays, repeated scans):
@@ -302,10 +304,12 @@ int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, in
    only then lets its own dependents start, so a producer kernel that itself uses programmatic
    dependent launch (and triggers early) is safe. */
 int amm_workspace_set_pipelined(amm_workspace* ws, int on);
-/* Small inputs take the one-pass latency kernel (exact per-element tracking, no second phase)
-   instead of the streaming kernel: by default up to 2^20 elements for 1/2/4-byte dtypes and
-   2^16 for 8-byte dtypes (the measured crossovers).  This call replaces that rule by "inputs of
-   at most `bytes`"; 0 disables the latency kernel. */
+/* Small inputs take the one-trip latency kernel (every thread holds its 1-4 vectors in registers:
+   value-only fold, then the first matching element is located in registers; nothing is re-read)
+   instead of the streaming kernel: by default up to 2^20 elements for 1/2/4-byte dtypes and 2^16
+   for 8-byte dtypes (the measured crossovers), and never more than four 16-byte vectors per
+   thread.  This call replaces the size rule by "inputs of at most `bytes`"; 0 disables the
+   latency kernel. */
 int amm_workspace_set_direct_threshold(amm_workspace* ws, uint64_t bytes);
 int amm_workspace_get_tuning(const amm_workspace* ws, int* threads, int* ctas_per_sm, int* variant,
                              int* sm_count);
