@@ -992,6 +992,25 @@ int amm_measure_call_latency(int dtype, const void* dev_ptr, uint64_t n, int mod
   return AMM_OK;
 }
 
+/* Pure host logic of the streaming kernel's tile plan, exposed for the CPU test-suite
+   (tests/test_scan_plan.py replays the kernel's index formulas on it).  out[0..11] = head_elems,
+   n_vec, tail_start, per_vecs, grid, n_full_tiles, rem_vecs, rem_owner, dyn_tiles, dyn_koff,
+   kind (0 grid-stride, 1 contiguous, 2 dynamic tail), status. */
+int amm_debug_plan_scan(uint64_t base_addr, uint64_t n, int elem_size, int vec_bytes, int u, int threads,
+                        uint64_t grid_cap, int sm_count, int pipelined, int scan_contig, int scan_dyn_pct,
+                        uint64_t out[12]) {
+  if (!out || n == 0 || threads < 32 || u < 1 || (vec_bytes != 16 && vec_bytes != 32) ||
+      (elem_size != 1 && elem_size != 2 && elem_size != 4 && elem_size != 8) || base_addr % (uint64_t)elem_size)
+    return AMM_ERR_ARG;
+  const ScanPlanKnobs knobs = {sm_count, scan_contig, scan_dyn_pct, 1};
+  const ScanPlan pl = plan_scan(base_addr, n, (uint32_t)elem_size, (uint32_t)vec_bytes, (uint32_t)u, (uint32_t)threads,
+                                grid_cap, pipelined != 0, knobs);
+  const uint64_t v[12] = {pl.head_elems, pl.n_vec, pl.tail_start, pl.per_vecs, pl.grid, pl.n_full_tiles,
+                          pl.rem_vecs, pl.rem_owner, pl.dyn_tiles, pl.dyn_koff, (uint64_t)pl.kind, (uint64_t)pl.status};
+  memcpy(out, v, sizeof(v));
+  return AMM_OK;
+}
+
 /* AMM_PHASE_STAMPS builds only (tools/phase_stamps.py): copies the %globaltimer stamps of the
    most recent scan, 8 words per CTA, for `ctas` CTAs.  Other builds: AMM_ERR_ARG. */
 int amm_debug_read_stamps(amm_workspace* ws, uint64_t* out, int ctas) {

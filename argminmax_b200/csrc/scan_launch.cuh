@@ -46,6 +46,93 @@ static cudaError_t launch_scan(Kernel kernel, unsigned grid, unsigned threads, c
   return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
+// ---------------------------------------------------------------------------------------
+// Tile plan of the streaming kernel: pure host arithmetic (unit-tested without a GPU through
+// amm_debug_plan_scan, tests/test_scan_plan.py, which replays the kernel's index formulas and
+// checks that every vector is visited exactly once).
+// ---------------------------------------------------------------------------------------
+struct ScanPlan {
+  uint64_t head_elems, n_vec, tail_start;  // unaligned head | whole vectors | sub-vector tail
+  uint64_t per_vecs;                       // CONTIGUOUS: vectors per CTA (multiple of threads), else 0
+  uint64_t grid;
+  uint32_t n_full_tiles;  // statically assigned full tiles
+  uint32_t rem_vecs;      // vectors of the one partial tile (behind all full tiles)
+  uint32_t rem_owner;     // GRID-STRIDE / DYNAMIC: the CTA that takes it
+  uint32_t dyn_tiles;     // DYNAMIC: full tiles claimed at run time (behind the static ones)
+  uint32_t dyn_koff;      // slot tile ids >= dyn_koff name claimed tiles (UINT32_MAX: none)
+  int kind;               // 0 grid-stride, 1 contiguous, 2 dynamic tail
+  int status;             // AMM_OK or AMM_ERR_TOO_LARGE
+};
+
+struct ScanPlanKnobs {
+  int sm_count;
+  int scan_contig;         // -1 automatic, 0 never, 1 always
+  int scan_dyn_pct;        // -1 automatic, 0 none, 1..90
+  int scan_dyn_pipelined;  // claimed tail also for pipelined scans (HBM-sized inputs only)
+};
+
+static ScanPlan plan_scan(uint64_t addr, uint64_t n, uint32_t es, uint32_t vec, uint32_t u, uint32_t threads,
+                          uint64_t grid_cap, bool pipelined, const ScanPlanKnobs& k) {
+  ScanPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  pl.dyn_koff = 0xFFFFFFFFu;
+  const uint64_t vec_elems = vec / es;
+  const uint64_t tile_vecs = (uint64_t)threads * u;
+  uint64_t head = ((vec - (addr % vec)) % vec) / es;
+  if (head > n) head = n;
+  pl.head_elems = head;
+  pl.n_vec = (n - head) / vec_elems;
+  pl.tail_start = head + pl.n_vec * vec_elems;
+  const uint64_t full = pl.n_vec / tile_vecs;
+  if ((2 * full + 4) * (uint64_t)u >= 0xFFFFFFFFull) {  // 32-bit slot ids
+    pl.status = AMM_ERR_TOO_LARGE;
+    return pl;
+  }
+  pl.n_full_tiles = (uint32_t)full;
+  pl.rem_vecs = (uint32_t)(pl.n_vec % tile_vecs);
+  const uint64_t tiles = full + (pl.rem_vecs ? 1 : 0);
+  uint64_t grid = grid_cap < 1 ? 1 : grid_cap;
+  // How the tiles are handed out (profiles/r02_fixed_cost.md).  CTAs given equal shares finish
+  // far apart -- the memory system serves them at very different rates (2.4x between the first
+  // and the last CTA at 40 MB, +-2.6 % at 4 GiB) and the stragglers then stream alone, latency-
+  // bound.  So, with at least two tiles per CTA:
+  //   DYNAMIC TAIL  the first tiles grid-stride, the last AMM_SCAN_DYN_PCT % claimed at run time
+  //                 (8 % on HBM-sized inputs -- more costs a barrier per tile for nothing --
+  //                 30 % below 0.5 GiB);
+  // otherwise
+  //   CONTIGUOUS    fewer than 64 tiles per CTA: equal ranges of whole rows (blockDim vectors);
+  //   GRID-STRIDE   else: whole tiles b, b + G, ... (the +-1 tile imbalance is noise there).
+  const bool big = n * es >= ((uint64_t)512 << 20);
+  const int dyn_pct = k.scan_dyn_pct >= 0 ? k.scan_dyn_pct : (big ? 8 : 30);
+  // (pipelined scans: only on HBM-sized inputs, +0.9 % at 4 GiB; below that the next scan's
+  // streaming already fills the gaps the stragglers leave and the claims only cost: 100 M u8
+  // 14.1 -> 15.4 us per call in a stream of calls)
+  const bool dynamic = dyn_pct > 0 && (!pipelined || (k.scan_dyn_pipelined && big)) && k.scan_contig != 1 &&
+                       full >= 2 * grid && grid >= (uint64_t)k.sm_count;
+  const bool contig = !dynamic && (k.scan_contig < 0 ? tiles < 64 * grid : k.scan_contig != 0);
+  if (dynamic) {
+    uint64_t dyn = full * (uint64_t)(dyn_pct > 90 ? 90 : dyn_pct) / 100;
+    if (dyn < grid) dyn = grid;  // one claim per CTA goes out on entry
+    pl.dyn_tiles = (uint32_t)dyn;
+    pl.n_full_tiles = (uint32_t)(full - dyn);
+    pl.dyn_koff = (uint32_t)((full - dyn + grid - 1) / grid + 1);
+    pl.kind = 2;
+  } else if (contig) {
+    const uint64_t rows = (pl.n_vec + (uint64_t)threads - 1) / (uint64_t)threads;
+    uint64_t rows_per_cta = (rows + grid - 1) / grid;
+    if (rows_per_cta < 1) rows_per_cta = 1;
+    grid = (rows + rows_per_cta - 1) / rows_per_cta;  // drops the CTAs that would get nothing
+    pl.per_vecs = rows_per_cta * (uint64_t)threads;
+    pl.kind = 1;
+  } else {
+    if (grid > tiles) grid = tiles;
+    pl.rem_owner = grid ? (uint32_t)(full % grid) : 0;
+    pl.kind = 0;
+  }
+  pl.grid = grid < 1 ? 1 : grid;
+  return pl;
+}
+
 template <class P, int VEC, int U, bool PF, int HINT, bool XCHG, bool PACKED>
 static int launch_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
                          cudaStream_t stream) {
@@ -61,62 +148,23 @@ static int launch_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, int v
     occ = o < 1 ? 1 : o;
     ws->occupancy_threads[dtype_slot][vslot] = threads;
   }
-  const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
-  const uint64_t tile_vecs = (uint64_t)threads * U;
-  // geometry: unaligned head | whole vectors | sub-vector tail
-  const uint64_t addr = (uint64_t)(uintptr_t)p.base;
-  uint64_t head = ((VEC - (addr % VEC)) % VEC) / sizeof(typename P::Elem);
-  if (head > p.n) head = p.n;
-  p.head_elems = head;
-  p.n_vec = (p.n - head) / vec_elems;
-  p.tail_start = head + p.n_vec * vec_elems;
-  const uint64_t full = p.n_vec / tile_vecs;
-  if ((2 * full + 4) * (uint64_t)U >= 0xFFFFFFFFull) return AMM_ERR_TOO_LARGE;  // 32-bit slot ids
-  p.n_full_tiles = (uint32_t)full;
-  p.rem_vecs = (uint32_t)(p.n_vec % tile_vecs);
-  const uint64_t tiles = full + (p.rem_vecs ? 1 : 0);
   int per_sm = ws->eff_ctas_per_sm < occ ? ws->eff_ctas_per_sm : occ;
-  uint64_t grid = (uint64_t)ws->sm_count * (uint64_t)per_sm;
-  if (grid > (uint64_t)ws->max_grid) grid = (uint64_t)ws->max_grid;
-  // How the tiles are handed out (profiles/r02_fixed_cost.md).  CTAs given equal shares finish
-  // far apart -- the memory system serves them at very different rates (2.4x between the first
-  // and the last CTA at 40 MB, +-2.6 % at 4 GiB) and the stragglers then stream alone, latency-
-  // bound.  So, with at least two tiles per CTA:
-  //   DYNAMIC TAIL  the first tiles grid-stride, the last AMM_SCAN_DYN_PCT % claimed at run time
-  //                 (8 % on HBM-sized inputs -- more costs a barrier per tile for nothing --
-  //                 30 % below 0.5 GiB);
-  // otherwise
-  //   CONTIGUOUS    fewer than 64 tiles per CTA: equal ranges of whole rows (blockDim vectors);
-  //   GRID-STRIDE   else: whole tiles b, b + G, ... (the +-1 tile imbalance is noise there).
-  p.per_vecs = 0;
-  p.dyn_tiles = 0;
-  p.dyn_koff = 0xFFFFFFFFu;
-  p.rem_owner = 0;
-  const bool big = p.n_bytes >= ((uint64_t)512 << 20);
-  const int dyn_pct = ws->scan_dyn_pct >= 0 ? ws->scan_dyn_pct : (big ? 8 : 30);
-  // (pipelined scans: only on HBM-sized inputs, +0.9 % at 4 GiB; below that the next scan's
-  // streaming already fills the gaps the stragglers leave and the claims only cost: 100 M u8
-  // 14.1 -> 15.4 us per call in a stream of calls)
-  const bool dynamic = dyn_pct > 0 && (!p.pipelined || (ws->scan_dyn_pipelined && big)) &&
-                       ws->scan_contig != 1 && full >= 2 * grid && grid >= (uint64_t)ws->sm_count;
-  const bool contig = !dynamic && (ws->scan_contig < 0 ? tiles < 64 * grid : ws->scan_contig != 0);
-  if (dynamic) {
-    uint64_t dyn = full * (uint64_t)(dyn_pct > 90 ? 90 : dyn_pct) / 100;
-    if (dyn < grid) dyn = grid;  // one claim per CTA goes out on entry
-    p.dyn_tiles = (uint32_t)dyn;
-    p.n_full_tiles = (uint32_t)(full - dyn);
-    p.dyn_koff = (uint32_t)((full - dyn + grid - 1) / grid + 1);
-  } else if (contig) {
-    const uint64_t rows = (p.n_vec + (uint64_t)threads - 1) / (uint64_t)threads;
-    uint64_t rows_per_cta = (rows + grid - 1) / grid;
-    if (rows_per_cta < 1) rows_per_cta = 1;
-    grid = (rows + rows_per_cta - 1) / rows_per_cta;  // drops the CTAs that would get nothing
-    p.per_vecs = rows_per_cta * (uint64_t)threads;
-  } else {
-    if (grid > tiles) grid = tiles;
-    p.rem_owner = grid ? (uint32_t)(full % grid) : 0;
-  }
-  if (grid < 1) grid = 1;
+  uint64_t grid_cap = (uint64_t)ws->sm_count * (uint64_t)per_sm;
+  if (grid_cap > (uint64_t)ws->max_grid) grid_cap = (uint64_t)ws->max_grid;
+  const ScanPlanKnobs knobs = {ws->sm_count, ws->scan_contig, ws->scan_dyn_pct, ws->scan_dyn_pipelined};
+  const ScanPlan pl = plan_scan((uint64_t)(uintptr_t)p.base, p.n, (uint32_t)sizeof(typename P::Elem), VEC, U,
+                                (uint32_t)threads, grid_cap, p.pipelined != 0, knobs);
+  if (pl.status) return pl.status;
+  p.head_elems = pl.head_elems;
+  p.n_vec = pl.n_vec;
+  p.tail_start = pl.tail_start;
+  p.n_full_tiles = pl.n_full_tiles;
+  p.rem_vecs = pl.rem_vecs;
+  p.rem_owner = pl.rem_owner;
+  p.per_vecs = pl.per_vecs;
+  p.dyn_tiles = pl.dyn_tiles;
+  p.dyn_koff = pl.dyn_koff;
+  const uint64_t grid = pl.grid;
   // With programmatic dependent launch the CTAs of the NEXT scan on the stream become resident
   // while this one runs.  If an SM can hold more than twice the CTAs a scan puts on it, the
   // block scheduler packs the next grid onto the free slots of fewer SMs (3 per SM instead of

@@ -332,6 +332,14 @@ int amm_debug_plan_window_chunks(const uint64_t* begins, const uint64_t* ends, u
                                  size_t elem_size, int sm_count, int chunks_per_sm,
                                  uint64_t* cuts_out, uint64_t cuts_capacity, uint64_t* n_cuts,
                                  uint64_t* first_out);
+/* Test hook (pure host logic, needs no GPU): the tile plan of the streaming kernel for an array
+   of `n` elements of `elem_size` bytes at address `base_addr`, vectors of `vec_bytes`, `u` vectors
+   per thread per tile, CTAs of `threads`, at most `grid_cap` CTAs.  out[0..11] = head_elems, n_vec,
+   tail_start, per_vecs, grid, n_full_tiles, rem_vecs, rem_owner, dyn_tiles, dyn_koff, kind
+   (0 grid-stride, 1 contiguous ranges, 2 grid-stride + claimed tail), status. */
+int amm_debug_plan_scan(uint64_t base_addr, uint64_t n, int elem_size, int vec_bytes, int u, int threads,
+                        uint64_t grid_cap, int sm_count, int pipelined, int scan_contig, int scan_dyn_pct,
+                        uint64_t out[12]);
 /* Debug twin built with -DAMM_PHASE_STAMPS only (tools/phase_stamps.py): %globaltimer stamps of
    the most recent scan, 8 words per CTA (entry, first tile folded, streaming done, CTA reduced,
    ticket taken; last CTA: grid folded, exact finish done, published).  The product library
