@@ -55,6 +55,18 @@ struct KeyLim<int64_t> {
   static constexpr int64_t MINV = INT64_MIN;
 };
 
+// compare domains of the window kernels for f32 / f64 (windows_kernel.cuh: WinCmp): +-infinity
+template <>
+struct KeyLim<float> {
+  static constexpr float MAXV = __builtin_huge_valf();
+  static constexpr float MINV = -__builtin_huge_valf();
+};
+template <>
+struct KeyLim<double> {
+  static constexpr double MAXV = __builtin_huge_val();
+  static constexpr double MINV = -__builtin_huge_val();
+};
+
 // --------------------------------------------------------------- 32-bit ints
 template <bool SIGNED>
 struct PolInt32 {

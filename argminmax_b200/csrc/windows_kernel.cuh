@@ -94,13 +94,80 @@ struct WindowGeom {
   }
 };
 
+// The domain in which the window kernels compare candidates.  By default the canonical
+// integer keys of the policy.  For f64 the VALUES themselves: turning a double into its ord key
+// (NaN test, -0.0 canonicalisation, 64-bit sign fold) costs ~10 instructions per key and a unit
+// needs two of them, more than the fold of the unit's four elements; comparing doubles is one
+// DSETP, orders -0.0 == +0.0 exactly like the canonical keys, and the key is only needed once per
+// window (to locate the winning element).  i64 windows ran at 5.0-5.9 TB/s where f64 ran at
+// 3.6-4.1 with the same loads and the same bookkeeping: the difference was `finish`.
+template <class P>
+struct WinCmp {
+  using T = typename P::Key;
+  static __device__ __forceinline__ T maxv() { return KeyLim<T>::MAXV; }
+  static __device__ __forceinline__ T minv() { return KeyLim<T>::MINV; }
+  static __device__ __forceinline__ void finish(const typename P::Acc& a, T& mn, T& mx, bool& valid, bool& has_nan) {
+    P::finish(a, mn, mx, valid, has_nan);
+  }
+  static __device__ __forceinline__ void classify(typename P::Elem raw, T& k, bool& valid, bool& is_nan) {
+    P::classify(raw, k, valid, is_nan);
+  }
+  static __device__ __forceinline__ typename P::Key to_key(T v) { return v; }
+};
+// f32: the same (the reference's scalar path compares f32 as IEEE values, -0.0 == +0.0; f16 does NOT
+// qualify -- the reference orders f16 through the i16 ord key, where -0.0 < +0.0)
+template <int MODE>
+struct WinCmp<PolF32<MODE>> {
+  using P = PolF32<MODE>;
+  using T = float;
+  static __device__ __forceinline__ T maxv() { return __int_as_float(0x7F800000); }
+  static __device__ __forceinline__ T minv() { return __int_as_float((int)0xFF800000u); }
+  static __device__ __forceinline__ void finish(const typename P::Acc& a, T& mn, T& mx, bool& valid, bool& has_nan) {
+    mn = a.mn;  // ignore: NaN only if every element was one; return: NaN if any was (min.NaN)
+    mx = a.mx;
+    const bool mn_nan = a.mn != a.mn;
+    has_nan = (MODE == MODE_RETURN) && mn_nan;
+    valid = !mn_nan;
+  }
+  static __device__ __forceinline__ void classify(uint32_t raw, T& k, bool& valid, bool& is_nan) {
+    k = __uint_as_float(raw);
+    is_nan = k != k;
+    valid = !is_nan;
+  }
+  static __device__ __forceinline__ int32_t to_key(T v) { return P::key(__float_as_uint(v)); }
+};
+template <int MODE>
+struct WinCmp<PolF64<MODE>> {
+  using P = PolF64<MODE>;
+  using T = double;
+  static __device__ __forceinline__ T maxv() { return __longlong_as_double(0x7FF0000000000000ll); }
+  static __device__ __forceinline__ T minv() { return __longlong_as_double((long long)0xFFF0000000000000ull); }
+  static __device__ __forceinline__ void finish(const typename P::Acc& a, T& mn, T& mx, bool& valid, bool& has_nan) {
+    mn = a.mn;  // fmin / fmax drop NaNs: NaN only if every element was one
+    mx = a.mx;
+    if constexpr (MODE == MODE_RETURN) {
+      has_nan = a.nan;
+      valid = !a.nan;
+    } else {
+      has_nan = false;
+      valid = a.mn == a.mn;
+    }
+  }
+  static __device__ __forceinline__ void classify(uint64_t raw, T& k, bool& valid, bool& is_nan) {
+    k = __longlong_as_double((long long)raw);
+    is_nan = k != k;
+    valid = !is_nan;
+  }
+  static __device__ __forceinline__ int64_t to_key(T v) { return key_f64((uint64_t)__double_as_longlong(v)); }
+};
+
 // value-only fold of this thread's share of the window; units are visited in ascending order
 template <class P, int STRIDE, int UN = 4, int VECB = 16>
 __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeom<P, VECB>& g,
-                                            uint32_t t, Best<typename P::Key>& x) {
+                                            uint32_t t, Best<typename WinCmp<P>::T>& x) {
   constexpr int NW = VECB / 4;
   using Elem = typename P::Elem;
-  using Key = typename P::Key;
+  using Key = typename WinCmp<P>::T;  // compare domain: the policy's keys, or doubles for f64
   const Elem* e = reinterpret_cast<const Elem*>(base);
   auto consider = [&](Key kmin, Key kmax, bool valid, bool has_nan, uint64_t unit) {
     if (valid && (kmin < x.kmin || x.pmin == POS_NONE)) {
@@ -116,7 +183,7 @@ __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeo
   for (uint32_t h = t; h < g.hc; h += STRIDE) {  // unit 0: the head, one element at a time
     Key k;
     bool valid, is_nan;
-    P::classify(e[g.begin + h], k, valid, is_nan);
+    WinCmp<P>::classify(e[g.begin + h], k, valid, is_nan);
     consider(k, k, valid, P::TRACK_NAN && is_nan, 0);
   }
   const uint8_t* vbase = base + g.a0 * sizeof(Elem);
@@ -137,7 +204,7 @@ __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeo
         for (int q = P::WPI; q < NW; q += P::WPI) P::feed(acc, &w[u][q]);
         Key kmin, kmax;
         bool valid, has_nan;
-        P::finish(acc, kmin, kmax, valid, has_nan);
+        WinCmp<P>::finish(acc, kmin, kmax, valid, has_nan);
         consider(kmin, kmax, valid, has_nan, v + 1);
       }
     }
@@ -145,7 +212,7 @@ __device__ __forceinline__ void window_fold(const uint8_t* base, const WindowGeo
   for (uint32_t q = t; q < g.tc; q += STRIDE) {  // unit nv+1: the tail
     Key k;
     bool valid, is_nan;
-    P::classify(e[g.a0 + g.nv * WindowGeom<P, VECB>::VE + q], k, valid, is_nan);
+    WinCmp<P>::classify(e[g.a0 + g.nv * WindowGeom<P, VECB>::VE + q], k, valid, is_nan);
     consider(k, k, valid, P::TRACK_NAN && is_nan, g.nv + 1);
   }
 }
@@ -206,8 +273,8 @@ __device__ __forceinline__ void window_locate_store(const WindowParams& p, uint6
 // window has fewer than 2^32 units) and without the NaN field for policies that do not track
 // NaNs: per-window cost matters when windows are a few hundred elements.
 template <class P, int G>
-__device__ __forceinline__ void window_group_reduce(Best<typename P::Key>& x) {
-  using Key = typename P::Key;
+__device__ __forceinline__ void window_group_reduce(Best<typename WinCmp<P>::T>& x) {
+  using Key = typename WinCmp<P>::T;
   Key kmin = x.kmin, kmax = x.kmax;
   uint32_t umin = (uint32_t)x.pmin, umax = (uint32_t)x.pmax, unan = (uint32_t)x.pnan;  // NONE -> ~0u
 #pragma unroll
@@ -236,6 +303,18 @@ __device__ __forceinline__ void window_group_reduce(Best<typename P::Key>& x) {
   x.pnan = (!P::TRACK_NAN || unan == 0xFFFFFFFFu) ? POS_NONE : (uint64_t)unan;
 }
 
+// compare-domain candidates -> canonical keys (what window_locate_store matches elements against)
+template <class P>
+__device__ __forceinline__ Best<typename P::Key> window_to_keys(const Best<typename WinCmp<P>::T>& x) {
+  Best<typename P::Key> k;
+  k.kmin = WinCmp<P>::to_key(x.kmin);
+  k.kmax = WinCmp<P>::to_key(x.kmax);
+  k.pmin = x.pmin;
+  k.pmax = x.pmax;
+  k.pnan = x.pnan;
+  return k;
+}
+
 // one group of G lanes per window (32 / G windows per warp), grid-stride over windows
 template <class P, int G, int VECB = 16>
 __global__ void __launch_bounds__(256) argminmax_windows_warp_kernel(const WindowParams p) {
@@ -251,11 +330,11 @@ __global__ void __launch_bounds__(256) argminmax_windows_warp_kernel(const Windo
     uint64_t begin = 0, end = 0;
     if (active) window_bounds<P>(p, w, begin, end);
     const WindowGeom<P, VECB> g(p.base, begin, end);
-    Best<Key> x;
+    Best<typename WinCmp<P>::T> x;
     x.clear();
     window_fold<P, G, 4, VECB>(p.base, g, lane % G, x);
     window_group_reduce<P, G>(x);
-    window_locate_store<P, G, VECB>(p, w, active, g, x, lane);
+    window_locate_store<P, G, VECB>(p, w, active, g, window_to_keys<P>(x), lane);
   }
 }
 
@@ -365,18 +444,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 
 // Running (key, unit) candidates of one lane; units are 32-bit (a window handled here has far
 // fewer than 2^32 units), 0xFFFFFFFF = none yet.
-template <typename Key>
+template <class P>
 struct WinBest {
-  Key kmin, kmax;
+  using T = typename WinCmp<P>::T;
+  T kmin, kmax;
   uint32_t umin, umax, unan;
   __device__ __forceinline__ void clear() {
-    kmin = KeyLim<Key>::MAXV;
-    kmax = KeyLim<Key>::MINV;
+    kmin = WinCmp<P>::maxv();
+    kmax = WinCmp<P>::minv();
     umin = umax = unan = 0xFFFFFFFFu;
   }
   // full lexicographic rule (units may arrive in any order)
   template <bool TRACK_NAN>
-  __device__ __forceinline__ void consider(Key k0, Key k1, bool valid, bool has_nan, uint32_t unit) {
+  __device__ __forceinline__ void consider(T k0, T k1, bool valid, bool has_nan, uint32_t unit) {
     if (valid && (k0 < kmin || (k0 == kmin && unit < umin))) {
       kmin = k0;
       umin = unit;
@@ -393,8 +473,8 @@ struct WinBest {
 // rotation so that the lanes of a quarter-warp do not all hit the same shared-memory banks
 template <class P, int L, bool STAGED>
 __device__ __forceinline__ void staged_fold_vectors(const WinSrc& src, uint32_t nv, uint32_t l,
-                                                    uint32_t wi, WinBest<typename P::Key>& x) {
-  using Key = typename P::Key;
+                                                    uint32_t wi, WinBest<P>& x) {
+  using CT = typename WinCmp<P>::T;
   const uint32_t cnt = nv > l ? (nv - l + L - 1) / L : 0;
   if (cnt == 0) return;
   uint32_t kk = STAGED ? wi % cnt : 0;  // rotation only matters for shared-memory banks
@@ -416,9 +496,9 @@ __device__ __forceinline__ void staged_fold_vectors(const WinSrc& src, uint32_t 
         P::init(acc, &wv[u][0]);
 #pragma unroll
         for (int q = P::WPI; q < 4; q += P::WPI) P::feed(acc, &wv[u][q]);
-        Key a, b;
+        CT a, b;
         bool valid, has_nan;
-        P::finish(acc, a, b, valid, has_nan);
+        WinCmp<P>::finish(acc, a, b, valid, has_nan);
         x.template consider<P::TRACK_NAN>(a, b, valid, has_nan, vv[u] + 1);
       }
     }
@@ -433,8 +513,8 @@ __device__ __forceinline__ void staged_fold_vectors(const WinSrc& src, uint32_t 
 // are issue-bound, not shared-memory-bound).
 template <class P, int L>
 __device__ __forceinline__ void staged_fold_pairs(const WinSrc& src, uint32_t nv, uint32_t l,
-                                                  uint32_t wi, WinBest<typename P::Key>& x) {
-  using Key = typename P::Key;
+                                                  uint32_t wi, WinBest<P>& x) {
+  using CT = typename WinCmp<P>::T;
   static_assert(sizeof(typename P::Elem) == 8, "pairs of vectors are for 8-byte elements");
   const uint32_t npairs = nv >> 1;
   const uint32_t cnt = npairs > l ? (npairs - l + L - 1) / L : 0;
@@ -461,9 +541,9 @@ __device__ __forceinline__ void staged_fold_pairs(const WinSrc& src, uint32_t nv
         P::feed(acc, &wv[u][0][2]);
         P::feed(acc, &wv[u][1][0]);
         P::feed(acc, &wv[u][1][2]);
-        Key a, b;
+        CT a, b;
         bool valid, has_nan;
-        P::finish(acc, a, b, valid, has_nan);
+        WinCmp<P>::finish(acc, a, b, valid, has_nan);
         x.template consider<P::TRACK_NAN>(a, b, valid, has_nan, pp[u] + 1);
       }
     }
@@ -474,9 +554,9 @@ __device__ __forceinline__ void staged_fold_pairs(const WinSrc& src, uint32_t nv
     typename P::Acc acc;
     P::init(acc, &w[0]);
     P::feed(acc, &w[2]);
-    Key a, b;
+    CT a, b;
     bool valid, has_nan;
-    P::finish(acc, a, b, valid, has_nan);
+    WinCmp<P>::finish(acc, a, b, valid, has_nan);
     x.template consider<P::TRACK_NAN>(a, b, valid, has_nan, npairs + 1);
   }
 }
@@ -654,7 +734,8 @@ __global__ void __launch_bounds__(THREADS)
     if (kp == 0) mbar_wait(&s_bar[s], (it >> 1) & 1);
 
     // ---- value-only fold of this lane's share of the window
-    WinBest<Key> x;
+    using CT = typename WinCmp<P>::T;
+    WinBest<P> x;
     x.clear();
     if constexpr (FAST) {
       if constexpr (sizeof(Elem) == 8) {
@@ -664,9 +745,9 @@ __global__ void __launch_bounds__(THREADS)
       }
     } else {
       for (uint32_t h = l; h < g.hc; h += L) {  // unit 0: unaligned head
-        Key k;
+        CT k;
         bool valid, is_nan;
-        P::classify(src.elem<Elem>(g.begin + h), k, valid, is_nan);
+        WinCmp<P>::classify(src.elem<Elem>(g.begin + h), k, valid, is_nan);
         x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, 0);
       }
       if (src.vec_staged) {
@@ -675,17 +756,17 @@ __global__ void __launch_bounds__(THREADS)
         staged_fold_vectors<P, L, false>(src, (uint32_t)g.nv, l, wi, x);
       }
       for (uint32_t q = l; q < g.tc; q += L) {  // unit nv+1: sub-vector tail
-        Key k;
+        CT k;
         bool valid, is_nan;
-        P::classify(src.elem<Elem>(g.a0 + g.nv * WindowGeom<P>::VE + q), k, valid, is_nan);
+        WinCmp<P>::classify(src.elem<Elem>(g.a0 + g.nv * WindowGeom<P>::VE + q), k, valid, is_nan);
         x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, (uint32_t)g.nv + 1);
       }
     }
     // ---- reduce inside the lane group (lexicographic on (key, unit))
 #pragma unroll
     for (int m = L / 2; m >= 1; m >>= 1) {
-      const Key okmin = __shfl_xor_sync(0xFFFFFFFFu, x.kmin, m);
-      const Key okmax = __shfl_xor_sync(0xFFFFFFFFu, x.kmax, m);
+      const CT okmin = __shfl_xor_sync(0xFFFFFFFFu, x.kmin, m);
+      const CT okmax = __shfl_xor_sync(0xFFFFFFFFu, x.kmax, m);
       const uint32_t oumin = __shfl_xor_sync(0xFFFFFFFFu, x.umin, m);
       const uint32_t oumax = __shfl_xor_sync(0xFFFFFFFFu, x.umax, m);
       if (okmin < x.kmin || (okmin == x.kmin && oumin < x.umin)) {
@@ -709,7 +790,7 @@ __global__ void __launch_bounds__(THREADS)
       const uint32_t unit = c == 0 ? x.umin : (c == 1 ? x.umax : x.unan);
       uint64_t r = POS_NONE;
       if (active && unit != 0xFFFFFFFFu && l == (uint32_t)(c % L))
-        r = staged_locate<P, FAST>(src, g, unit, c, c == 0 ? x.kmin : x.kmax);
+        r = staged_locate<P, FAST>(src, g, unit, c, WinCmp<P>::to_key(c == 0 ? x.kmin : x.kmax));
       if (L > 1) r = __shfl_sync(0xFFFFFFFFu, r, (int)(lane - l) + (c % L));
       res[c] = r;
     }
@@ -835,12 +916,13 @@ __global__ void __launch_bounds__(THREADS)
     mbar_wait(&s_bar[s], (it >> 1) & 1);
 
     // ---- value-only fold of this lane's share: unit 0 = head, 1..nv = vectors, nv + 1 = tail
-    WinBest<Key> x;
+    using CT = typename WinCmp<P>::T;
+    WinBest<P> x;
     x.clear();
     for (uint32_t h = l; h < hc; h += L) {
-      Key k;
+      CT k;
       bool valid, is_nan;
-      P::classify(lds_elem<Elem>(s_head + h * ES), k, valid, is_nan);
+      WinCmp<P>::classify(lds_elem<Elem>(s_head + h * ES), k, valid, is_nan);
       x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, 0);
     }
     constexpr bool PAIRS = ES == 8;  // 8-byte dtypes: a vector unit is a pair of vectors
@@ -851,16 +933,16 @@ __global__ void __launch_bounds__(THREADS)
       staged_fold_vectors<P, L, true>(src, nv, l, wi, x);
     }
     for (uint32_t q = l; q < tc; q += L) {
-      Key k;
+      CT k;
       bool valid, is_nan;
-      P::classify(lds_elem<Elem>(s_tail + q * ES), k, valid, is_nan);
+      WinCmp<P>::classify(lds_elem<Elem>(s_tail + q * ES), k, valid, is_nan);
       x.template consider<P::TRACK_NAN>(k, k, valid, is_nan, nvu + 1);
     }
     // ---- reduce inside the lane group (lexicographic on (key, unit))
 #pragma unroll
     for (int m = L / 2; m >= 1; m >>= 1) {
-      const Key okmin = __shfl_xor_sync(0xFFFFFFFFu, x.kmin, m);
-      const Key okmax = __shfl_xor_sync(0xFFFFFFFFu, x.kmax, m);
+      const CT okmin = __shfl_xor_sync(0xFFFFFFFFu, x.kmin, m);
+      const CT okmax = __shfl_xor_sync(0xFFFFFFFFu, x.kmax, m);
       const uint32_t oumin = __shfl_xor_sync(0xFFFFFFFFu, x.umin, m);
       const uint32_t oumax = __shfl_xor_sync(0xFFFFFFFFu, x.umax, m);
       if (okmin < x.kmin || (okmin == x.kmin && oumin < x.umin)) {
@@ -918,7 +1000,8 @@ __global__ void __launch_bounds__(THREADS)
     for (int c = 0; c < NC; ++c) {
       const uint32_t unit = c == 0 ? x.umin : (c == 1 ? x.umax : x.unan);
       uint32_t r = 0xFFFFFFFFu;
-      if (active && unit != 0xFFFFFFFFu && l == (uint32_t)(c % L)) r = locate(unit, c, c == 0 ? x.kmin : x.kmax);
+      if (active && unit != 0xFFFFFFFFu && l == (uint32_t)(c % L))
+        r = locate(unit, c, WinCmp<P>::to_key(c == 0 ? x.kmin : x.kmax));
       if (L > 1) r = __shfl_sync(0xFFFFFFFFu, r, (int)(lane - l) + (c % L));
       res[c] = r;
     }
@@ -998,17 +1081,17 @@ __global__ void __launch_bounds__(256) argminmax_windows_combine_kernel(const Wi
 // one CTA per window (large windows)
 template <class P, int THREADS, int UN, int VECB = 16>
 __global__ void __launch_bounds__(THREADS) argminmax_windows_cta_kernel(const WindowParams p) {
-  using Key = typename P::Key;
-  __shared__ Best<Key> smem[32];
+  using CT = typename WinCmp<P>::T;
+  __shared__ Best<CT> smem[32];
   for (uint64_t w = blockIdx.x; w < p.n_windows; w += gridDim.x) {
     uint64_t begin, end;
     window_bounds<P>(p, w, begin, end);
     const WindowGeom<P, VECB> g(p.base, begin, end);
-    Best<Key> x;
+    Best<CT> x;
     x.clear();
     window_fold<P, THREADS, UN, VECB>(p.base, g, threadIdx.x, x);  // THREADS * UN * VECB bytes in flight
     x = block_reduce(x, smem);
-    if (threadIdx.x < 32) window_locate_store<P, 32, VECB>(p, w, true, g, x, threadIdx.x);
+    if (threadIdx.x < 32) window_locate_store<P, 32, VECB>(p, w, true, g, window_to_keys<P>(x), threadIdx.x);
   }
 }
 
