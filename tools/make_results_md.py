@@ -21,7 +21,7 @@ def one(name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tag", default="r02e")
-    ap.add_argument("--multi-tag", default="r02d")
+    ap.add_argument("--multi-tag", default="r02g")
     a = ap.parse_args()
     t = a.tag
     out = []
@@ -104,25 +104,25 @@ def main():
       f"{s['f32_100m']['gbs']} GB/s; 100 M u8 {s['u8_100m']['us']} µs; 102 400 f32 {s['f32_102400']['us']} µs (device time) |")
     w("")
 
-    w(f"## Config 5 — 32 Gi f32 (128 GiB) sharded, weak and strong scaling (`profiles/{a.multi_tag}_bench_n{{4,8}}.json`, `r02c_bench_n2.json`)\n")
+    w(f"## Config 5 — 32 Gi f32 (128 GiB) sharded, weak and strong scaling (`profiles/{a.multi_tag}_bench_n{{2,4,8}}.json`, one 8-GPU box)\n")
     w("| GPUs | weak: aggregate GB/s (4 GiB per GPU) | ms/step | strong: 2^30 elements in total, ms per serialised call | efficiency vs 1 GPU (serialised / pipelined) | 32 Gi elements in total | e2e from host, GB/s (× plain-copy ceiling) | in-process `amm_sharded_argminmax`, µs/call (peer / NCCL) |")
     w("|---:|---:|---:|---:|---:|---:|---:|---:|")
     w(f"| 1 | {b1['value']} | {b1['ms_per_step']} | {rf['kernel_ms']} | – | – | {e['value']} ({e['frac_of_h2d_ceiling']}) | – |")
-    for n, name in ((2, "r02c_bench_n2.json"), (4, f"{a.multi_tag}_bench_n4.json"), (8, f"{a.multi_tag}_bench_n8.json")):
+    for n, name in ((2, f"{a.multi_tag}_bench_n2.json"), (4, f"{a.multi_tag}_bench_n4.json"), (8, f"{a.multi_tag}_bench_n8.json")):
         try:
             d = one(name)
         except OSError:
             continue
         st, c5, ee, ip = d["strong"], d["config5"], d["e2e"], d["sharded_in_process"]
         w(f"| {n} | {d['value']} | {d['ms_per_step']} | {st['ms']} ({st['gbs']} GB/s) | {st['efficiency_vs_n1']} / "
-          f"{st['efficiency_vs_n1_pipelined']} | {c5['ms']} ms, {c5['gbs']} GB/s | {ee['value']} | "
+          f"{st['efficiency_vs_n1_pipelined']} | {c5['ms']} ms, {c5['gbs']} GB/s | {ee['value']} ({ee['frac_of_h2d_ceiling']}) | "
           f"{ip['peer']['us_per_call']} / {ip['nccl']['us_per_call']} |")
     w("\nEvery multi-GPU line was produced after its parity step passed (duplicate extremes in the first and the last shard, "
       "NaNs in return mode, an empty shard, all-equal; in-process check of both exchanges; `multi_gpu_parity`, "
-      "`sharded_in_process` in the line). Per-GPU indices exceed 2^32 in the 32 Gi rows. The `e2e` fractions of the "
-      "recorded 4- and 8-GPU lines (0.98 / 0.72) were computed against a ceiling whose repetitions were not started "
-      "together; measured lock-step the plain copies give 115 / 185–187 GB/s and the host-slice call 115 / 187 "
-      "(`r02d_h2d_{4,8}gpu_plain_vs_host_slice.jsonl`) — `bench.py` now measures the ceiling that way.\n")
+      "`sharded_in_process` in the line). Per-GPU indices exceed 2^32 in the 32 Gi rows. The plain-copy ceiling is measured "
+      "in the same run with all N ranks pulling pinned host memory at once, started together (N x bytes / slowest rank): "
+      "at 8 GPUs four GPUs get 23 GB/s and four 36 (55.6 alone) -- the host side of PCIe, not the pipeline "
+      "(`r02d_h2d_{4,8}gpu_plain_vs_host_slice.jsonl`).\n")
     try:
         d8 = one(f"{a.multi_tag}_bench_n8.json")
         w("Synchronous collective call vs the single-GPU call on the same total size, 8 GPUs, µs (median, timed inside the library): "

@@ -18,6 +18,8 @@ def main():
     ap.add_argument("--dtypes", default="f32,u8,f16,f64")
     ap.add_argument("--windows", default="64,256,1000,4096,20000,1000000")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--ragged", action="store_true",
+                    help="ragged windows (offsets): lengths uniform in [W/2, 3W/2], the down-sampling-by-time case")
     a = ap.parse_args()
     g = torch.Generator(device="cuda:0").manual_seed(3)
     t = torch.empty(a.bytes // 4, dtype=torch.int32, device="cuda:0")
@@ -28,16 +30,26 @@ def main():
     for dt in a.dtypes.split(","):
         ds = amm.DeviceSlice.from_torch(raw, dtype=dt, workspace=ws, stream=stream)
         for w in [int(x) for x in a.windows.split(",")]:
+            arg = w
+            if a.ragged:
+                n = ds.n
+                nwin = max(1, n // w)
+                lens = torch.randint(max(1, w // 2), w + w // 2 + 1, (nwin,), device="cuda:0", dtype=torch.int64, generator=g)
+                offs = torch.zeros(nwin + 1, dtype=torch.int64, device="cuda:0")
+                torch.cumsum(lens, 0, out=offs[1:])
+                offs = torch.clamp(offs, max=n)
+                offs[-1] = n
+                arg = offs
             for _ in range(2):
-                out = ds.argminmax_windows(w)
+                out = ds.argminmax_windows(arg)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(a.iters):
-                out = ds.argminmax_windows(w)
+                out = ds.argminmax_windows(arg)
             e1.record()
             e1.synchronize()
             ms = e0.elapsed_time(e1) / a.iters
-            print(json.dumps({"dtype": dt, "window": w, "n_windows": out.shape[0], "ms": round(ms, 4),
+            print(json.dumps({"dtype": dt, "window": w, "ragged": bool(a.ragged), "n_windows": out.shape[0], "ms": round(ms, 4),
                               "GBps": round(a.bytes / ms / 1e6, 1)}), flush=True)
 
 
