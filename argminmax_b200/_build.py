@@ -15,7 +15,8 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libargminmax_b200.so")
 STAMP = os.path.join(LIB_DIR, "build.stamp")
 SOURCES = ["libamm.cu", "host_slice.cu", "sharded.cu", "scan_inst.cu"]
-HEADERS = ["amm_internal.h", "record_slot.h", "policies.cuh", "scan_kernel.cuh", "scan_launch.cuh", "windows_kernel.cuh",
+HEADERS = ["amm_internal.h", "record_slot.h", "policies.cuh", "scan_kernel.cuh", "ring_kernel.cuh", "scan_launch.cuh",
+           "windows_kernel.cuh",
            os.path.join("..", "..", "include", "argminmax_b200.h")]
 N_GROUPS = 7  # scan_inst.cu is compiled once per policy group (-DAMM_GROUP=k), in parallel
 NVCC_FLAGS = [

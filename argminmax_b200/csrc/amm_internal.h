@@ -40,6 +40,7 @@ struct amm_workspace {
   int direct_threads, direct_ctas_per_sm;
   int direct_vecs_per_thread;  // target vectors per thread when sizing the latency kernel's grid
   int direct_packed;      // 32-bit keys: packed-word atomics instead of partials (AMM_DIRECT_PACKED=0: off)
+  int direct_one_cta_vecs;  // inputs of up to this many 16-byte vectors (and 16 Ki elements) take ONE CTA
   int scan_packed;        // the same cross-CTA step in the streaming kernel (AMM_SCAN_PACKED=0: off)
   int scan_dyn_pct;       // share of the tiles claimed at run time: -1 automatic, 0 none, 1..90 percent (AMM_SCAN_DYN_PCT)
   int scan_ring;          // TMA-ring kernel: -1 automatic (inputs >= 512 MiB), 0 never, 1 always (AMM_SCAN_RING)
@@ -54,8 +55,8 @@ struct amm_workspace {
   size_t dyn_smem_set[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // MaxDynamicSharedMemorySize set so far
   size_t smem_per_sm, smem_reserved_per_cta, smem_optin_per_cta;  // device limits (co-residency cap)
   void* partials;            // max_grid x 64 B
-  uint32_t* ticket;          // 128 words: [0] last-block-done counter (self-resetting), [8] bounds-check
-                             // errors, [16..21] packed candidate words, [64..127] claim-counter ring
+  uint32_t* ticket;          // scratch block of WS_SCRATCH_BYTES: ticket, bounds-check errors, claim-counter
+                             // ring, packed candidate words (layout: scan_kernel.cuh, WS_*)
   amm_record* rec_dev;       // device record slot
   amm_record* rec_host;      // pinned + mapped host slot: record + checksum word (128 B)
   amm_record* rec_host_dev;  // ... its device address

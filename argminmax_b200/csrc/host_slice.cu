@@ -178,6 +178,7 @@ static int host_scan(int dtype, const void* host_ptr, uint64_t n, int mode, uint
     p->child[i]->direct_bytes = ws->direct_bytes;
     p->child[i]->direct_auto = ws->direct_auto;
     p->child[i]->direct_packed = ws->direct_packed;
+    p->child[i]->direct_one_cta_vecs = ws->direct_one_cta_vecs;
     p->child[i]->direct_vecs_per_thread = ws->direct_vecs_per_thread;
     p->child[i]->direct_elems32 = ws->direct_elems32;
     p->child[i]->direct_elems64 = ws->direct_elems64;

@@ -318,6 +318,7 @@ static int workspace_init(amm_workspace* ws, int device) {
   if (getenv("AMM_DIRECT_THREADS")) ws->direct_threads = atoi(getenv("AMM_DIRECT_THREADS"));
   if (getenv("AMM_DIRECT_CTAS")) ws->direct_ctas_per_sm = atoi(getenv("AMM_DIRECT_CTAS"));
   ws->direct_packed = getenv("AMM_DIRECT_PACKED") ? atoi(getenv("AMM_DIRECT_PACKED")) : 1;
+  ws->direct_one_cta_vecs = getenv("AMM_DIRECT_ONE_CTA_VECS") ? atoi(getenv("AMM_DIRECT_ONE_CTA_VECS")) : 2048;
   ws->scan_packed = getenv("AMM_SCAN_PACKED") ? atoi(getenv("AMM_SCAN_PACKED")) : 1;
   ws->scan_contig = getenv("AMM_SCAN_CONTIG") ? atoi(getenv("AMM_SCAN_CONTIG")) : -1;
   ws->scan_dyn_pct = getenv("AMM_SCAN_DYN_PCT") ? atoi(getenv("AMM_SCAN_DYN_PCT")) : -1;
@@ -345,15 +346,17 @@ static int workspace_init(amm_workspace* ws, int device) {
   ws->win_lane_bytes = getenv("AMM_WIN_LANE_BYTES") ? atoi(getenv("AMM_WIN_LANE_BYTES")) : 128;
   if (ws->win_lane_bytes < 16 || ws->win_lane_bytes > 1024) ws->win_lane_bytes = 128;
   ws->max_grid = ws->sm_count * 32;
-  // partials sized for the widest Best<int64_t> (40 B) -> 64 B slots
+  // one 64-byte tagged slot per CTA (grid_reduce: five words + integrity word).  Zeroed: recycled
+  // memory may hold a destroyed workspace's slots, whose sequence numbers also started at 1
   AMM_CUDA(cudaMalloc(&ws->partials, (size_t)ws->max_grid * 64));
-  AMM_CUDA(cudaMalloc((void**)&ws->ticket, 512));
-  AMM_CUDA(cudaMemset(ws->ticket, 0, 512));
-  // words of the ticket block: [0] ticket, [8] bounds-check error count, [16..21] packed candidate
-  // words, [64..127] claim counters of the dynamic tail (ring indexed by the call's seq)
+  AMM_CUDA(cudaMemset(ws->partials, 0, (size_t)ws->max_grid * 64));
+  AMM_CUDA(cudaMalloc((void**)&ws->ticket, WS_SCRATCH_BYTES));  // layout: scan_kernel.cuh, WS_*
+  AMM_CUDA(cudaMemset(ws->ticket, 0, WS_SCRATCH_BYTES));
   {  // packed candidate words start at their identities (packed_grid_reduce)
     const unsigned long long ident[3] = {PACK_MIN_NONE, PACK_MAX_NONE, POS_NONE};
-    AMM_CUDA(cudaMemcpy(ws->ticket + 16, ident, sizeof(ident), cudaMemcpyHostToDevice));
+    const uint32_t at[3] = {WS_PACK_MIN, WS_PACK_MAX, WS_PACK_NAN};
+    for (int i = 0; i < 3; ++i)
+      AMM_CUDA(cudaMemcpy(ws->ticket + at[i], &ident[i], sizeof(ident[i]), cudaMemcpyHostToDevice));
   }
   AMM_CUDA(cudaMalloc((void**)&ws->rec_dev, sizeof(amm_record)));
   AMM_CUDA(cudaMemset(ws->rec_dev, 0, sizeof(amm_record)));

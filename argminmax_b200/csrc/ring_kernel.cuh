@@ -51,7 +51,6 @@ __global__ void __launch_bounds__(RING_THREADS) argminmax_ring_kernel(const Scan
   static_assert(!PACKED || sizeof(Key) == 4, "packed candidates need 32-bit keys");
   extern __shared__ __align__(128) uint8_t ring[];  // RING_STAGES x RING_TILE_BYTES
   __shared__ ReduceScratch<Key> scratch;
-  __shared__ uint32_t s_is_last;
   __shared__ __align__(8) uint64_t s_full[RING_STAGES], s_empty[RING_STAGES];
   __shared__ uint32_t s_tile[RING_STAGES];
   pdl_entry(p);
@@ -59,7 +58,7 @@ __global__ void __launch_bounds__(RING_THREADS) argminmax_ring_kernel(const Scan
   const uint8_t* main_base = p.base + p.head_elems * sizeof(typename P::Elem);
   const Bounds bd(p);
   const uint32_t n_tiles = p.n_full_tiles;  // whole 32 KiB tiles, all claimed at run time
-  uint32_t* const claim = p.ticket + 64 + (uint32_t)(p.seq & 63ull);  // ring of counters, see scan_kernel.cuh
+  uint32_t* const claim = p.ticket + WS_CLAIM_RING + (uint32_t)(p.seq & 63ull);  // ring of counters, see scan_kernel.cuh
 
   if (threadIdx.x == 0) {
 #pragma unroll
@@ -178,8 +177,7 @@ __global__ void __launch_bounds__(RING_THREADS) argminmax_ring_kernel(const Scan
     b.pnan = vnan;
     b = block_reduce(b, scratch.best());
     stamp(p, ST_CTA_REDUCED);
-    if (!grid_reduce(p, b, scratch.best(), &s_is_last)) return;
-    if (threadIdx.x >= 32) return;
+    if (!grid_reduce(p, b, scratch.best())) return;
   }
   // every CTA has taken its ticket, hence made its last claim: re-arm the claim counter
   if (threadIdx.x == 0) *claim = 0u;

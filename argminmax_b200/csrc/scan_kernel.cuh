@@ -32,6 +32,8 @@
 #pragma once
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/argminmax_b200.h"
 #include "policies.cuh"
 #include "record_slot.h"
@@ -41,6 +43,7 @@ namespace amm {
 constexpr uint32_t TILE_NONE = 0xFFFFFFFFu;  // "no slot yet" in the per-thread running state
 constexpr uint64_t POS_NONE = 0xFFFFFFFFFFFFFFFFull;
 constexpr int MAX_THREADS = 512;
+constexpr int DIRECT_MAX_THREADS = 512;
 
 struct ScanParams {
   const uint8_t* base;     // caller's device pointer (element 0)
@@ -74,6 +77,19 @@ struct ScanParams {
   uint64_t* stamps;            // AMM_PHASE_STAMPS builds: gridDim.x x 8 %globaltimer stamps (else unused)
 };
 
+// 32-bit words of the workspace's scratch block (`ticket`, WS_SCRATCH_BYTES, zero-initialised except
+// the packed words): the ticket, the packed candidate words and the claim counters are hit by up
+// to 592 CTAs within a microsecond; the ticket and each packed word sit on their own 128-byte
+// line (measured: no faster than sharing the ticket's line, profiles/r02_fixed_cost.md -- kept
+// because it cannot hurt).
+constexpr uint32_t WS_TICKET = 0;        // last-block-done counter (self-resetting)
+constexpr uint32_t WS_BOUNDS_ERR = 8;    // AMM_BOUNDS_CHECK builds: out-of-range loads seen
+constexpr uint32_t WS_CLAIM_RING = 64;   // 64 claim counters of the dynamic tile schedule, indexed by seq & 63
+constexpr uint32_t WS_PACK_MIN = 128;    // packed candidate words (packed_grid_reduce), 64 bits each
+constexpr uint32_t WS_PACK_MAX = 160;
+constexpr uint32_t WS_PACK_NAN = 192;
+constexpr size_t WS_SCRATCH_BYTES = 1024;
+
 // Debug builds (-DAMM_BOUNDS_CHECK, argminmax_b200/_build.py:build_boundscheck) verify that every global load of input
 // data lies inside [base, base + n_bytes); violations are counted in a scratch word and
 // surface as AMM_REC_BOUNDS in the record (compute-sanitizer is not available on the pool).
@@ -83,7 +99,7 @@ struct Bounds {
   const uint8_t* hi;
   uint32_t* err;
   __device__ __forceinline__ explicit Bounds(const ScanParams& p)
-      : lo(p.base), hi(p.base + p.n_bytes), err(p.ticket + 8) {}
+      : lo(p.base), hi(p.base + p.n_bytes), err(p.ticket + WS_BOUNDS_ERR) {}
   __device__ __forceinline__ void check(const void* ptr, uint32_t bytes) const {
     const uint8_t* a = static_cast<const uint8_t*>(ptr);
     if (a < lo || a + bytes > hi) atomicAdd(err, 1u);
@@ -162,11 +178,69 @@ __device__ __forceinline__ Best<Key> shfl_xor(const Best<Key>& b, int lane_mask)
   return o;
 }
 
+// The warp's smallest / largest key among the lanes that have one (one redux for 32-bit keys, two
+// for 64-bit keys: high words, then low words among the lanes that match).  Lanes without a key
+// must still call; without any key in the warp the result is the identity.
+template <typename Key>
+__device__ __forceinline__ Key warp_min_key(bool has, Key k) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  if constexpr (sizeof(Key) == 4) {
+    return (Key)(__reduce_min_sync(FULL, has ? (uint32_t)k ^ 0x80000000u : 0xFFFFFFFFu) ^ 0x80000000u);
+  } else {
+    const uint64_t b = has ? (uint64_t)k ^ 0x8000000000000000ull : ~0ull;
+    const uint32_t hi = (uint32_t)(b >> 32), lo = (uint32_t)b;
+    const uint32_t mh = __reduce_min_sync(FULL, hi);
+    const uint32_t ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xFFFFFFFFu);
+    return (Key)((((uint64_t)mh << 32) | ml) ^ 0x8000000000000000ull);
+  }
+}
+template <typename Key>
+__device__ __forceinline__ Key warp_max_key(bool has, Key k) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  if constexpr (sizeof(Key) == 4) {
+    return (Key)(__reduce_max_sync(FULL, has ? (uint32_t)k ^ 0x80000000u : 0u) ^ 0x80000000u);
+  } else {
+    const uint64_t b = has ? (uint64_t)k ^ 0x8000000000000000ull : 0ull;
+    const uint32_t hi = (uint32_t)(b >> 32), lo = (uint32_t)b;
+    const uint32_t mh = __reduce_max_sync(FULL, hi);
+    const uint32_t ml = __reduce_max_sync(FULL, hi == mh ? lo : 0u);
+    return (Key)((((uint64_t)mh << 32) | ml) ^ 0x8000000000000000ull);
+  }
+}
+
+__device__ __forceinline__ uint64_t warp_min_u64(uint64_t v) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const uint32_t hi = (uint32_t)(v >> 32), lo = (uint32_t)v;
+  const uint32_t mh = __reduce_min_sync(FULL, hi);
+  const uint32_t ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xFFFFFFFFu);
+  return ((uint64_t)mh << 32) | ml;
+}
+
+// Warp-wide lexicographic reduce of (key, position) candidates; every lane gets the result.
+// Integer keys: the warp integer min/max instruction (redux.sync) on 32-bit pieces -- key, then
+// position among the lanes that hold that key: 8-10 instructions where five shuffle rounds over
+// five 64-bit words were ~250 (the code size of a latency kernel is part of its latency).
+// Floating-point keys (window kernels, value-domain compares): shuffles.
+template <typename Key>
+__device__ __forceinline__ void warp_reduce_best(Best<Key>& b) {
+  if constexpr (std::is_integral<Key>::value) {
+    const bool hmin = b.pmin != POS_NONE, hmax = b.pmax != POS_NONE;
+    const Key km = warp_min_key(hmin, b.kmin), kM = warp_max_key(hmax, b.kmax);
+    b.pmin = warp_min_u64((hmin && b.kmin == km) ? b.pmin : POS_NONE);
+    b.pmax = warp_min_u64((hmax && b.kmax == kM) ? b.pmax : POS_NONE);
+    b.kmin = km;
+    b.kmax = kM;
+    b.pnan = warp_min_u64(b.pnan);
+  } else {
+#pragma unroll 1
+    for (int m = 16; m >= 1; m >>= 1) b.merge(shfl_xor(b, m));
+  }
+}
+
 // All threads of the CTA must call; every thread returns the CTA-wide result.
 template <typename Key>
 __device__ __forceinline__ Best<Key> block_reduce(Best<Key> b, Best<Key>* smem /* [32] */) {
-#pragma unroll
-  for (int m = 16; m >= 1; m >>= 1) b.merge(shfl_xor(b, m));
+  warp_reduce_best(b);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarps = (blockDim.x + 31) >> 5;
   __syncthreads();  // smem may still be read from a previous call
@@ -176,8 +250,7 @@ __device__ __forceinline__ Best<Key> block_reduce(Best<Key> b, Best<Key>* smem /
     Best<Key> t;
     t.clear();
     if (lane < nwarps) t = smem[lane];
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) t.merge(shfl_xor(t, m));
+    warp_reduce_best(t);
     if (lane == 0) smem[0] = t;
   }
   __syncthreads();
@@ -353,7 +426,7 @@ __device__ __forceinline__ amm_record make_record(const ScanParams& p, const Bes
   r.nan_idx = has_nan ? x.pnan + p.global_offset : AMM_NO_INDEX;
   r.flags = (has_value ? AMM_REC_HAS_VALUE : 0ull) | (has_nan ? AMM_REC_HAS_NAN : 0ull);
 #ifdef AMM_BOUNDS_CHECK
-  if (atomicExch(p.ticket + 8, 0u) != 0u) r.flags |= AMM_REC_BOUNDS;
+  if (atomicExch(p.ticket + WS_BOUNDS_ERR, 0u) != 0u) r.flags |= AMM_REC_BOUNDS;
 #endif
   r.n = p.n;
   r.seq = p.seq;
@@ -506,39 +579,96 @@ __device__ __forceinline__ void pdl_entry(const ScanParams& p) {
   }
 }
 
-// Cross-CTA reduce: every CTA deposits its Best, the last one to arrive (ticket) folds them.
-// Returns true in the last CTA only, with `b` = grid-wide result.  gridDim.x == 1 skips the
-// round trip through global memory.
+// Cross-CTA step for candidates that do not fit one 64-bit word (64-bit keys): TAGGED SLOTS.
+// Every CTA but CTA 0 stores its CTA-wide Best -- five 64-bit words plus an integrity word seeded
+// with the call's sequence number and the slot index -- into its own 64-byte slot of `partials` and
+// exits; CTA 0 polls the slots (every thread one or two at a time, all loads in flight together),
+// accepts a slot when its integrity word matches, and folds them.  One one-way trip through L2 plus
+// a poll, where "store partial, fence, ticket, last CTA: fence, load all partials" was three
+// dependent round trips (tools/exp/latency_floor.cu, 4 MiB skeleton: 9.8 -> 8.5 us per call).  No
+// fence and no atomicity assumption beyond aligned 64-bit words: a slot that is torn, or still
+// holds an older call's record, fails the integrity check and is polled again.  CTA 0 holds one
+// CTA slot of the GPU while it polls and every other CTA runs to completion without waiting, so
+// grids larger than the GPU are fine.
+// Returns true in warp 0 of CTA 0 only (all 32 lanes), with `b` = the grid-wide result.  `b` must
+// be the CTA-wide result in every thread (block_reduce) on entry.
+constexpr uint64_t GRID_SLOT_SEED = 0xC0FFEE0DD5107ull;
+__device__ __forceinline__ uint64_t grid_slot_check(const uint64_t (&w)[5], uint64_t seq, uint32_t slot) {
+  uint64_t c = GRID_SLOT_SEED ^ seq ^ ((uint64_t)slot << 48);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    c = (c ^ w[i]) * 0x9E3779B97F4A7C15ull;
+    c = (c << 23) | (c >> 41);
+    c += (uint64_t)(i + 1);
+  }
+  return c | 1ull;  // never 0: a zeroed slot (fresh workspace) cannot pass
+}
+
 template <typename Key>
-__device__ __forceinline__ bool grid_reduce(const ScanParams& p, Best<Key>& b, Best<Key>* smem,
-                                            uint32_t* s_is_last) {
+__device__ __forceinline__ bool grid_reduce(const ScanParams& p, Best<Key>& b, Best<Key>* smem) {
   pdl_wait_prior_grid();  // from here on the workspace is ours
-  if (gridDim.x == 1) return true;
-  Best<Key>* partials = reinterpret_cast<Best<Key>*>(p.partials);
-  if (threadIdx.x == 0) {
-    partials[blockIdx.x] = b;
-    __threadfence();
-    const uint32_t ticket = atomicInc(p.ticket, gridDim.x - 1);  // wraps to 0: reusable
-    *s_is_last = (ticket == gridDim.x - 1);
+  if (gridDim.x == 1) return threadIdx.x < 32;
+  uint64_t* const slots = reinterpret_cast<uint64_t*>(p.partials);  // gridDim.x x 8 words
+  if (blockIdx.x != 0) {
+    if (threadIdx.x == 0) {
+      const uint64_t w[5] = {(uint64_t)(int64_t)b.kmin, (uint64_t)(int64_t)b.kmax, b.pmin, b.pmax, b.pnan};
+      uint64_t* dst = slots + (uint64_t)blockIdx.x * 8;
+      asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w[0]), "l"(w[1]) : "memory");
+      asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 2), "l"(w[2]), "l"(w[3]) : "memory");
+      asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst + 4), "l"(w[4]),
+                   "l"(grid_slot_check(w, p.seq, blockIdx.x))
+                   : "memory");
+    }
+    stamp(p, ST_TICKET);
+    return false;
   }
   stamp(p, ST_TICKET);
-  __syncthreads();
-  if (!*s_is_last) return false;
-  __threadfence();
-  Best<Key> g;
-  g.clear();
-  for (uint32_t i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+  Best<Key> g = b;
+  for (uint32_t s0 = 1 + threadIdx.x; s0 < gridDim.x; s0 += 2 * blockDim.x) {
+    const uint32_t s1 = s0 + blockDim.x;
+    const bool two = s1 < gridDim.x;
+    uint64_t w0[6], w1[6];
+    bool ok0 = false, ok1 = !two;
+    while (!(ok0 && ok1)) {
+      if (!ok0) {
+        const uint64_t* src = slots + (uint64_t)s0 * 8;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0[2 * i]), "=l"(w0[2 * i + 1]) : "l"(src + 2 * i) : "memory");
+      }
+      if (!ok1) {
+        const uint64_t* src = slots + (uint64_t)s1 * 8;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+          asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w1[2 * i]), "=l"(w1[2 * i + 1]) : "l"(src + 2 * i) : "memory");
+      }
+      if (!ok0) {
+        const uint64_t d[5] = {w0[0], w0[1], w0[2], w0[3], w0[4]};
+        ok0 = grid_slot_check(d, p.seq, s0) == w0[5];
+      }
+      if (!ok1) {
+        const uint64_t d[5] = {w1[0], w1[1], w1[2], w1[3], w1[4]};
+        ok1 = grid_slot_check(d, p.seq, s1) == w1[5];
+      }
+    }
     Best<Key> o;
-    const Best<Key>* src = partials + i;
-    o.kmin = __ldcg(&src->kmin);
-    o.kmax = __ldcg(&src->kmax);
-    o.pmin = __ldcg(&src->pmin);
-    o.pmax = __ldcg(&src->pmax);
-    o.pnan = __ldcg(&src->pnan);
+    o.kmin = (Key)(int64_t)w0[0];
+    o.kmax = (Key)(int64_t)w0[1];
+    o.pmin = w0[2];
+    o.pmax = w0[3];
+    o.pnan = w0[4];
     g.merge(o);
+    if (two) {
+      o.kmin = (Key)(int64_t)w1[0];
+      o.kmax = (Key)(int64_t)w1[1];
+      o.pmin = w1[2];
+      o.pmax = w1[3];
+      o.pnan = w1[4];
+      g.merge(o);
+    }
   }
   b = block_reduce(g, smem);
-  return true;
+  return threadIdx.x < 32;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -551,7 +681,7 @@ __device__ __forceinline__ bool grid_reduce(const ScanParams& p, Best<Key>& b, B
 // CTA loads and reduces them" this removes one global round trip and one CTA-wide reduce from the
 // dependent chain (tools/exp/latency_floor.cu: 9.4 -> 8.1 us for the skeleton of a 4 MiB scan).
 // Positions are element indices in the latency kernel and vector indices in the streaming
-// kernel.  Words: p.ticket + 16 (min), + 18 (max), + 20 (NaN).
+// kernel.  Words: p.ticket + WS_PACK_MIN / WS_PACK_MAX / WS_PACK_NAN.
 // ---------------------------------------------------------------------------------------
 constexpr unsigned long long PACK_MIN_NONE = ~0ull;
 constexpr unsigned long long PACK_MAX_NONE = 0ull;
@@ -577,11 +707,11 @@ struct PackedCand {
   template <bool TRACK_NAN>
   __device__ __forceinline__ void warp_reduce() {
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    const bool has = pmin != PACK_POS_NONE;  // pmin and pmax are set together
-    const uint32_t km = __reduce_min_sync(FULL, has ? kmin : 0xFFFFFFFFu);
-    const uint32_t kM = __reduce_max_sync(FULL, has ? kmax : 0u);
-    const uint32_t pm = __reduce_min_sync(FULL, (has && kmin == km) ? pmin : PACK_POS_NONE);
-    const uint32_t pM = __reduce_min_sync(FULL, (has && kmax == kM) ? pmax : PACK_POS_NONE);
+    // a lane without a min (max) candidate holds the identity key and PACK_POS_NONE
+    const uint32_t km = __reduce_min_sync(FULL, kmin);
+    const uint32_t kM = __reduce_max_sync(FULL, kmax);
+    const uint32_t pm = __reduce_min_sync(FULL, kmin == km ? pmin : PACK_POS_NONE);
+    const uint32_t pM = __reduce_min_sync(FULL, kmax == kM ? pmax : PACK_POS_NONE);
     kmin = km;
     kmax = kM;
     pmin = pm;
@@ -595,6 +725,8 @@ struct PackedCand {
     if (pmin != PACK_POS_NONE) {
       g.kmin = (int32_t)(kmin ^ 0x80000000u);
       g.pmin = pmin;
+    }
+    if (pmax != PACK_POS_NONE) {
       g.kmax = (int32_t)(kmax ^ 0x80000000u);
       g.pmax = pmax;
     }
@@ -638,19 +770,19 @@ __device__ __forceinline__ bool packed_grid_reduce(const ScanParams& p, PackedCa
   if (lane == 0) {
     pdl_wait_prior_grid();  // from here on the workspace is ours
     if (gridDim.x > 1) {
-      unsigned long long* words = reinterpret_cast<unsigned long long*>(p.ticket + 16);
-      if (c.pmin != PACK_POS_NONE) {
-        atomicMin(&words[0], ((unsigned long long)c.kmin << 32) | c.pmin);
-        atomicMax(&words[1], ((unsigned long long)c.kmax << 32) | (uint32_t)~c.pmax);
-      }
-      if (P::TRACK_NAN && c.pnan != PACK_POS_NONE) atomicMin(&words[2], (unsigned long long)c.pnan);
+      unsigned long long* const word_min = reinterpret_cast<unsigned long long*>(p.ticket + WS_PACK_MIN);
+      unsigned long long* const word_max = reinterpret_cast<unsigned long long*>(p.ticket + WS_PACK_MAX);
+      unsigned long long* const word_nan = reinterpret_cast<unsigned long long*>(p.ticket + WS_PACK_NAN);
+      if (c.pmin != PACK_POS_NONE) atomicMin(word_min, ((unsigned long long)c.kmin << 32) | c.pmin);
+      if (c.pmax != PACK_POS_NONE) atomicMax(word_max, ((unsigned long long)c.kmax << 32) | (uint32_t)~c.pmax);
+      if (P::TRACK_NAN && c.pnan != PACK_POS_NONE) atomicMin(word_nan, (unsigned long long)c.pnan);
       __threadfence();
-      last = atomicInc(p.ticket, gridDim.x - 1) == gridDim.x - 1;
+      last = atomicInc(p.ticket + WS_TICKET, gridDim.x - 1) == gridDim.x - 1;
       if (last) {
         __threadfence();
-        wmin = atomicExch(&words[0], PACK_MIN_NONE);  // read the grid-wide result and re-arm
-        wmax = atomicExch(&words[1], PACK_MAX_NONE);
-        if (P::TRACK_NAN) wnan = atomicExch(&words[2], POS_NONE);
+        wmin = atomicExch(word_min, PACK_MIN_NONE);  // read the grid-wide result and re-arm
+        wmax = atomicExch(word_max, PACK_MAX_NONE);
+        if (P::TRACK_NAN) wnan = atomicExch(word_nan, POS_NONE);
       }
     }
   }
@@ -665,6 +797,8 @@ __device__ __forceinline__ bool packed_grid_reduce(const ScanParams& p, PackedCa
     if (wmin != PACK_MIN_NONE) {
       c.kmin = (uint32_t)(wmin >> 32);
       c.pmin = (uint32_t)wmin;
+    }
+    if (wmax != PACK_MAX_NONE) {
       c.kmax = (uint32_t)(wmax >> 32);
       c.pmax = ~(uint32_t)wmax;
     }
@@ -683,22 +817,68 @@ struct alignas(16) ReduceScratch {
   __device__ __forceinline__ uint32_t* words() { return reinterpret_cast<uint32_t*>(raw); }
 };
 
+// Index (within a 16-byte vector held in registers) of the first element whose key equals `want`
+// -- the key of a non-NaN element known to be in the vector -- and of the first NaN.
+template <class P, int NW>
+__device__ __forceinline__ int locate_key(const uint32_t (&w)[NW], typename P::Key want) {
+  constexpr int VE = NW * 4 / (int)sizeof(typename P::Elem);
+  if constexpr (P::SIMD_EQ) {  // 8-bit ints, f16: packed equality compare + find-first-set
+    return vec_first_eq<P>(w, want);
+  } else {
+    int found = 0;
+#pragma unroll
+    for (int e = VE - 1; e >= 0; --e) {
+      typename P::Key k;
+      bool valid, nan;
+      P::classify(vec_elem<P, NW>(w, e), k, valid, nan);
+      found = (valid && k == want) ? e : found;
+    }
+    return found;
+  }
+}
+template <class P, int NW>
+__device__ __forceinline__ int locate_nan(const uint32_t (&w)[NW]) {
+  constexpr int VE = NW * 4 / (int)sizeof(typename P::Elem);
+  int found = 0;
+#pragma unroll
+  for (int e = VE - 1; e >= 0; --e) {
+    typename P::Key k;
+    bool valid, nan;
+    P::classify(vec_elem<P, NW>(w, e), k, valid, nan);
+    found = nan ? e : found;
+  }
+  return found;
+}
+
+// out = w[u] for a run-time u (selects over the register array: no local memory, no branches)
+template <int UN, int NW>
+__device__ __forceinline__ void select_vec(const uint32_t (&w)[UN][NW], int u, uint32_t (&out)[NW]) {
+#pragma unroll
+  for (int q = 0; q < NW; ++q) {
+    uint32_t v = w[0][q];
+#pragma unroll
+    for (int k = 1; k < UN; ++k) v = (u == k) ? w[k][q] : v;
+    out[q] = v;
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // Small inputs (up to a few MB): latency, not bandwidth, is what a caller sees.  ONE trip: every
 // thread loads its 1..4 vectors (16 B each, `direct_vpt` per thread, all in flight at once) and
 // keeps them in registers; value-only fold per vector exactly as in the streaming kernel, the
 // best vector per direction is remembered by its register slot, and the first matching element is
-// then located IN REGISTERS -- no index is carried per element and nothing is re-read.  The
-// dependent chain is load -> fold + locate -> CTA reduce -> grid step -> publish.
+// then located IN REGISTERS -- no index is carried per element and nothing is re-read -- and
+// LAZILY: only by the one or two lanes of a warp that hold the warp's best key (all 32 lanes
+// walking their four vectors cost 0.3-0.9 us per call).  The dependent chain is
+// load -> fold -> warp redux -> locate -> CTA reduce -> grid step -> publish.
 // ---------------------------------------------------------------------------------------
 template <class P, bool XCHG, bool PACKED = false>
-__global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(DIRECT_MAX_THREADS) argminmax_direct_kernel(const ScanParams p) {
   using Key = typename P::Key;
   using Elem = typename P::Elem;
   constexpr int VEC = 16, NW = 4, UN = 4;
   constexpr int VE = VEC / sizeof(Elem);
   __shared__ ReduceScratch<Key> scratch;
-  __shared__ uint32_t s_is_last;
   pdl_entry(p);
   stamp(p, ST_ENTRY);
   const uint8_t* main_base = p.base + p.head_elems * sizeof(Elem);
@@ -714,6 +894,9 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
     if (have[u]) {
       bd.check(main_base + vi * VEC, VEC);
       VecLoad<VEC>::ld(main_base + vi * VEC, w[u]);
+    } else {
+#pragma unroll
+      for (int q = 0; q < NW; ++q) w[u][q] = 0u;  // never selected (select_vec), but defined
     }
   }
   // value-only fold per vector; vectors ascend with u, so a strict compare keeps the first
@@ -739,58 +922,103 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
     }
   }
   stamp(p, ST_FIRST_FOLD);
-  // locate the first matching element inside the winning vectors (registers only)
+  // Locate the first matching element inside the winning vectors (registers only) -> (key, element
+  // index) candidates in `x`.  One vector per thread (the usual latency case): one fused pass over
+  // its elements.  Several: the winning vector is picked out of the register array with selects, so
+  // there is one copy of the locate code per direction (code size is latency here); with three or
+  // four vectors the warp first agrees on its best keys (one or two redux each) and only the lanes
+  // that hold one go on (LAZY: 1 Mi f32 -0.4..-0.6 us per call); with two, every lane locates in
+  // its own winners (the redux round trips in front would cost more than they save).
   Best<Key> x;
   x.clear();
-#pragma unroll
-  for (int u = 0; u < UN; ++u) {
-    const bool is_min = (u == umin), is_max = (u == umax), is_nan = P::TRACK_NAN && (u == unan);
-    if (is_min || is_max || is_nan) {
-      int emin = VE, emax = VE, enan = VE;
-      if constexpr (P::SIMD_EQ) {  // 8- / 16-bit elements: packed equality compare + find-first-set
-        if (is_min) emin = vec_first_eq<P>(w[u], bkmin);
-        if (is_max) emax = vec_first_eq<P>(w[u], bkmax);
-        if (is_nan) {
+  {
+    const uint64_t i0 = p.head_elems + v0 * VE;  // element index of vector u: i0 + u * blockDim * VE
+    const bool hv = umin >= 0;                   // umin and umax are set together
+    const uint32_t vnan = unan >= 0 ? (uint32_t)v0 + (uint32_t)unan * blockDim.x : PACK_POS_NONE;
+    if (vpt == 1) {
+      // the usual latency case, one vector per thread: one fused pass over its elements
+      if (hv || (P::TRACK_NAN && unan >= 0)) {
+        int emin = 0, emax = 0, enan = 0;
+        if constexpr (P::SIMD_EQ) {
+          emin = vec_first_eq<P>(w[0], bkmin);
+          emax = vec_first_eq<P>(w[0], bkmax);
+          if (P::TRACK_NAN) enan = locate_nan<P, NW>(w[0]);
+        } else {
 #pragma unroll
           for (int e = VE - 1; e >= 0; --e) {
             Key k;
             bool valid, nan;
-            P::classify(vec_elem<P, NW>(w[u], e), k, valid, nan);
-            enan = nan ? e : enan;
+            P::classify(vec_elem<P, NW>(w[0], e), k, valid, nan);
+            emin = (valid && k == bkmin) ? e : emin;
+            emax = (valid && k == bkmax) ? e : emax;
+            if (P::TRACK_NAN) enan = nan ? e : enan;
           }
         }
-      } else {
-#pragma unroll
-        for (int e = VE - 1; e >= 0; --e) {
-          Key k;
-          bool valid, nan;
-          P::classify(vec_elem<P, NW>(w[u], e), k, valid, nan);
-          emin = (valid && k == bkmin) ? e : emin;
-          emax = (valid && k == bkmax) ? e : emax;
-          if (P::TRACK_NAN) enan = nan ? e : enan;
+        if (hv) {
+          x.kmin = bkmin;
+          x.pmin = i0 + (uint64_t)emin;
+          x.kmax = bkmax;
+          x.pmax = i0 + (uint64_t)emax;
         }
+        if (P::TRACK_NAN && unan >= 0) x.pnan = i0 + (uint64_t)enan;
       }
-      const uint64_t i0 = p.head_elems + (v0 + (uint64_t)u * blockDim.x) * VE;
-      if (is_min) {
+    } else {
+      Key wkmin = bkmin, wkmax = bkmax;
+      uint32_t vfirst = vnan;
+      if (vpt >= 3) {
+        wkmin = warp_min_key(hv, bkmin);
+        wkmax = warp_max_key(hv, bkmax);
+        // vectors ascend with the address: the lane whose NaN vector comes first holds the first NaN
+        if (P::TRACK_NAN) vfirst = __reduce_min_sync(0xFFFFFFFFu, vnan);
+      }
+      uint32_t sel[NW];
+      if (hv && bkmin == wkmin) {
+        select_vec<UN, NW>(w, umin, sel);
         x.kmin = bkmin;
-        x.pmin = i0 + emin;
+        x.pmin = i0 + (uint64_t)umin * blockDim.x * VE + (uint64_t)locate_key<P, NW>(sel, bkmin);
       }
-      if (is_max) {
+      if (hv && bkmax == wkmax) {
+        select_vec<UN, NW>(w, umax, sel);
         x.kmax = bkmax;
-        x.pmax = i0 + emax;
+        x.pmax = i0 + (uint64_t)umax * blockDim.x * VE + (uint64_t)locate_key<P, NW>(sel, bkmax);
       }
-      if (is_nan) x.pnan = i0 + enan;
+      if (P::TRACK_NAN && unan >= 0 && vnan == vfirst) {
+        select_vec<UN, NW>(w, unan, sel);
+        x.pnan = i0 + (uint64_t)unan * blockDim.x * VE + (uint64_t)locate_nan<P, NW>(sel);
+      }
     }
   }
-  // unaligned head / sub-vector tail (< 16 B each): lexicographic merges, any order
-  if (blockIdx.x == 0) exact_range<P, false>(bd, p.base, 0, p.head_elems, x);
-  if (blockIdx.x == gridDim.x - 1) exact_range<P, false>(bd, p.base, p.tail_start, p.n, x);
+  // unaligned head / sub-vector tail (< 16 B each, first / last CTA): one element per thread,
+  // lexicographic merges
+  {
+    const bool in_head = blockIdx.x == 0 && threadIdx.x < p.head_elems;
+    const uint64_t it = p.tail_start + threadIdx.x;
+    const bool in_tail = blockIdx.x == gridDim.x - 1 && it < p.n;
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+      const bool on = part == 0 ? in_head : in_tail;
+      const uint64_t i = part == 0 ? (uint64_t)threadIdx.x : it;
+      if (on) {
+        const Elem* e = reinterpret_cast<const Elem*>(p.base);
+        bd.check(&e[i], sizeof(Elem));
+        Key k;
+        bool valid, is_nan;
+        P::classify(e[i], k, valid, is_nan);
+        if (valid) {
+          x.merge_min(k, i);
+          x.merge_max(k, i);
+        }
+        if (P::TRACK_NAN && is_nan && i < x.pnan) x.pnan = i;
+      }
+    }
+  }
   stamp(p, ST_STREAM_DONE);
   if constexpr (PACKED) {
     static_assert(sizeof(Key) == 4, "packed candidates need 32-bit keys");
     PackedCand c;
     c.clear();
-    if (x.pmin != POS_NONE) c.set(x.kmin, (uint32_t)x.pmin, x.kmax, (uint32_t)x.pmax);
+    if (x.pmin != POS_NONE) c.kmin = (uint32_t)x.kmin ^ 0x80000000u, c.pmin = (uint32_t)x.pmin;
+    if (x.pmax != POS_NONE) c.kmax = (uint32_t)x.kmax ^ 0x80000000u, c.pmax = (uint32_t)x.pmax;
     if (P::TRACK_NAN && x.pnan != POS_NONE) c.pnan = (uint32_t)x.pnan;
     if (!packed_grid_reduce<P>(p, c, scratch.words())) return;
     stamp(p, ST_GRID_FOLDED);
@@ -799,8 +1027,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_direct_kernel(const Sca
   } else {
     x = block_reduce(x, scratch.best());
     stamp(p, ST_CTA_REDUCED);
-    if (!grid_reduce(p, x, scratch.best(), &s_is_last)) return;
-    if (threadIdx.x >= 32) return;
+    if (!grid_reduce(p, x, scratch.best())) return;
     stamp(p, ST_GRID_FOLDED);
     stamp(p, ST_EXACT_DONE);
     finalize_warp<XCHG>(p, x);
@@ -911,7 +1138,6 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   constexpr int NW = VL::NW;
   static_assert(!PACKED || sizeof(Key) == 4, "packed candidates need 32-bit keys");
   __shared__ ReduceScratch<Key> scratch;
-  __shared__ uint32_t s_is_last;
   pdl_entry(p);
   stamp(p, ST_ENTRY);
 
@@ -959,7 +1185,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   // per SM at most).
   __shared__ uint32_t s_claim[2];
   const uint32_t dyn_tiles = p.dyn_tiles;
-  uint32_t* const dyn_counter = p.ticket + 64 + (uint32_t)(p.seq & 63ull);
+  uint32_t* const dyn_counter = p.ticket + WS_CLAIM_RING + (uint32_t)(p.seq & 63ull);
   uint32_t pending = 0;
   if (dyn_tiles != 0 && threadIdx.x == 0) pending = atomicAdd(dyn_counter, 1u);
   auto next_tile = [&](uint32_t i, const uint8_t*& q, uint32_t& t) -> bool {
@@ -1114,8 +1340,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
     b.pnan = vnan;
     b = block_reduce(b, scratch.best());
     stamp(p, ST_CTA_REDUCED);
-    if (!grid_reduce(p, b, scratch.best(), &s_is_last)) return;
-    if (threadIdx.x >= 32) return;
+    if (!grid_reduce(p, b, scratch.best())) return;
   }
   // every CTA has taken its ticket, hence made its last claim: re-arm the claim counter
   if (dyn_tiles != 0 && threadIdx.x == 0) *dyn_counter = 0u;

@@ -285,14 +285,21 @@ static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) 
   p.head_elems = head;
   p.n_vec = (p.n - head) / vec_elems;
   p.tail_start = head + p.n_vec * vec_elems;
-  const uint64_t threads = (uint64_t)ws->direct_threads;
+  uint64_t threads = (uint64_t)ws->direct_threads;
   // Latency, not throughput: as long as CTAs are available every thread gets ONE vector (more
   // CTAs are free latency); beyond sm_count x direct_ctas_per_sm CTAs threads take 2..4 vectors,
-  // all in flight at once.  Up to 4 vectors per thread ONE CTA is quicker than several: a second
-  // CTA brings in the cross-CTA round trip (~1.3 us).
+  // all in flight at once.  Small inputs take ONE CTA -- 256 threads up to 1024 vectors, 512
+  // threads up to direct_one_cta_vecs (2048 vectors = 32 KiB) and 16 Ki elements: a second CTA
+  // brings in the cross-CTA round trip (~1 us; in-process A/B, profiles/r02g_latency_ab.jsonl:
+  // 8 Ki f32 9.65 -> 8.6 us, 16 Ki f16 9.85 -> 8.9, 4 Ki i64 10.5 -> 9.2).  Few deep threads beat
+  // many shallow ones (4 Ki f32: 8.6 us as 256 x 4, 9.4 as 1024 x 1), but one SM folding 64 KiB is
+  // no faster than 16 SMs plus the round trip (u8 x 64 Ki in one CTA: 11.1 us against 9.3).
   const uint64_t cap = (uint64_t)ws->sm_count * (uint64_t)ws->direct_ctas_per_sm;
   uint64_t vpt = (p.n_vec + cap * threads - 1) / (cap * threads);
   if (vpt < (uint64_t)ws->direct_vecs_per_thread) vpt = (uint64_t)ws->direct_vecs_per_thread;
+  if (p.n_vec > threads * 4 && p.n_vec <= (uint64_t)ws->direct_one_cta_vecs &&
+      p.n_vec <= (uint64_t)DIRECT_MAX_THREADS * 4 && p.n <= 16384)
+    threads = DIRECT_MAX_THREADS;
   if (p.n_vec <= threads * 4) vpt = (p.n_vec + threads - 1) / threads;
   if (vpt < 1) vpt = 1;
   if (vpt > 4) return AMM_ERR_ARG;  // launch_variant checks direct_fits() first

@@ -261,3 +261,25 @@ def test_default_stream_with_another_current_device():
     finally:
         torch.cuda.set_device(0)
     ds._ws.close()
+
+
+@pytest.mark.parametrize("dt", ["i64", "f64", "f32"])
+def test_fresh_workspace_on_recycled_memory(dt):
+    """A workspace's per-CTA slots (grid step of the 64-bit-key kernels) are validated by an
+    integrity word seeded with the call's sequence number -- and every workspace starts counting
+    at 1.  A new workspace that gets a destroyed one's memory back must not accept the old slots:
+    same sizes, same sequence numbers, different data, workspaces created and destroyed in turn."""
+    from argminmax_b200 import Workspace
+    rng = np.random.default_rng(123)
+    n = 3_000_000
+    arrays = [random_array(dt, n, rng) for _ in range(4)]
+    slices = [to_device(a) for a in arrays]
+    expect = [oracle.argminmax(a, 0) for a in arrays]
+    for rep in range(6):
+        ws = Workspace(0)
+        for k in range(3):
+            i = (rep + k) % len(arrays)
+            ds = slices[i][0]
+            ds._ws = ws
+            assert ds.argminmax() == expect[i], (rep, k)
+        ws.close()

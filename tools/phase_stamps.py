@@ -37,11 +37,14 @@ def main():
     ap.add_argument("--threads", type=int, default=0)
     ap.add_argument("--ctas", type=int, default=0)
     ap.add_argument("--variant", type=int, default=-1)
+    ap.add_argument("--direct", action="store_true", help="keep the library's kernel choice (latency kernel for small n)")
+    ap.add_argument("--copies", type=int, default=0, help="rotating buffers (1 = L2-resident input); 0 = enough for 512 MB")
     a = ap.parse_args()
     lib = amm.lib()
     ws = amm.Workspace(0)
     ws.set_tuning(a.threads, a.ctas, a.variant)
-    ws.set_direct_threshold(0)  # streaming kernel only
+    if not a.direct:
+        ws.set_direct_threshold(0)  # streaming kernel only
     stream = torch.cuda.current_stream().cuda_stream
     g = torch.Generator(device="cuda:0").manual_seed(5)
     for case in a.cases.split(","):
@@ -51,6 +54,8 @@ def main():
         copies = max(2, -(-(512 << 20) // (n * es)))
         if n * es >= (1 << 30):
             copies = 1
+        if a.copies > 0:
+            copies = a.copies
         bufs = []
         for _ in range(copies):
             t = torch.empty((n * es + 3) // 4, dtype=torch.int32, device="cuda:0")
