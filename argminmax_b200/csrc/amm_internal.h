@@ -39,7 +39,7 @@ struct amm_workspace {
   int direct_auto;        // ... unless 1: size rule per key width (see launch_variant)
   int direct_threads, direct_ctas_per_sm;
   int direct_vecs_per_thread;  // target vectors per thread when sizing the latency kernel's grid
-  int direct_packed;      // 32-bit keys: packed-word atomics instead of partials (AMM_DIRECT_PACKED=0: off)
+  int direct_packed;      // 32-bit keys: packed-word atomics instead of tagged slots (AMM_DIRECT_PACKED=0: off)
   int direct_one_cta_vecs;  // inputs of up to this many 16-byte vectors (and 16 Ki elements) take ONE CTA
   int scan_packed;        // the same cross-CTA step in the streaming kernel (AMM_SCAN_PACKED=0: off)
   int scan_dyn_pct;       // share of the tiles claimed at run time: -1 automatic, 0 none, 1..90 percent (AMM_SCAN_DYN_PCT)
@@ -54,7 +54,7 @@ struct amm_workspace {
   size_t static_smem[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];   // static smem of the kernel + 1 (0 = not queried)
   size_t dyn_smem_set[AMM_POLICY_SLOTS][AMM_MAX_VARIANTS];  // MaxDynamicSharedMemorySize set so far
   size_t smem_per_sm, smem_reserved_per_cta, smem_optin_per_cta;  // device limits (co-residency cap)
-  void* partials;            // max_grid x 64 B
+  void* partials;            // max_grid x 64 B tagged slots, zeroed at creation (grid_reduce)
   uint32_t* ticket;          // scratch block of WS_SCRATCH_BYTES: ticket, bounds-check errors, claim-counter
                              // ring, packed candidate words (layout: scan_kernel.cuh, WS_*)
   amm_record* rec_dev;       // device record slot

@@ -327,7 +327,9 @@ static int workspace_init(amm_workspace* ws, int device) {
   if (ws->ring_ctas_per_sm < 1 || ws->ring_ctas_per_sm > 2) ws->ring_ctas_per_sm = 2;
   ws->scan_dyn_pipelined = getenv("AMM_SCAN_DYN_PIPELINED") ? atoi(getenv("AMM_SCAN_DYN_PIPELINED")) : 1;
   ws->direct_elems32 = getenv("AMM_DIRECT_ELEMS32") ? strtoull(getenv("AMM_DIRECT_ELEMS32"), nullptr, 10) : (1ull << 20);
-  ws->direct_elems64 = getenv("AMM_DIRECT_ELEMS64") ? strtoull(getenv("AMM_DIRECT_ELEMS64"), nullptr, 10) : (1ull << 16);
+  // 64-bit keys: 2^19 elements (4 MiB, the most the one-trip kernel holds) since its CTA reduce and grid
+  // step were rebuilt (in-process A/B: i64 x 2^18 10.8 -> 10.2 us, x 2^19 11.7 -> 10.8; 2^16 before)
+  ws->direct_elems64 = getenv("AMM_DIRECT_ELEMS64") ? strtoull(getenv("AMM_DIRECT_ELEMS64"), nullptr, 10) : (1ull << 19);
   ws->xtimeout_ms = getenv("AMM_PEER_TIMEOUT_MS") ? strtoull(getenv("AMM_PEER_TIMEOUT_MS"), nullptr, 10) : 60000;
   ws->direct_vecs_per_thread = getenv("AMM_DIRECT_VPT") ? atoi(getenv("AMM_DIRECT_VPT")) : 1;
   if (ws->direct_vecs_per_thread < 1 || ws->direct_vecs_per_thread > 16) ws->direct_vecs_per_thread = 1;

@@ -1,7 +1,7 @@
 // ring_kernel.cuh -- the HBM-sized scan fed through a TMA ring (sm_100a).
 //
 // Same algorithm as argminmax_scan_kernel (value-only fold per 16-byte vector, slot ids, packed /
-// partials grid step, warp-level exact finish, fused exchange), different data path:
+// tagged-slot grid step, warp-level exact finish, fused exchange), different data path:
 //
 //   * one PRODUCER thread per CTA (lane 0 of an extra warp) claims 32 KiB tiles from the
 //     workspace's claim counter -- every tile of the array, not just a tail: the claim costs the
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(RING_THREADS) argminmax_ring_kernel(const Scan
     stamp(p, ST_CTA_REDUCED);
     if (!grid_reduce(p, b, scratch.best())) return;
   }
-  // every CTA has taken its ticket, hence made its last claim: re-arm the claim counter
+  // every CTA has passed the grid step, hence made its last claim: re-arm the claim counter
   if (threadIdx.x == 0) *claim = 0u;
   stamp(p, ST_GRID_FOLDED);
   const Best<Key> x = exact_finish_warp<P, VEC_ELEMS>(p, bd, b);

@@ -19,10 +19,12 @@
 //    vectors visited in ascending order => earliest vector per thread).  No index
 //    lanes, hence no index overflow and none of the reference's restart loop; the loop
 //    is branch-free and its cost does not depend on the data order.
-//  * CTA reduce (warp shuffles, then shared memory) and the cross-CTA reduce
-//    (last-block-done ticket) are lexicographic on (key, global vector index): the
-//    earliest vector that contains the global extreme wins.
-//  * One warp of the last CTA finishes exactly: the winning min / max / first-NaN
+//  * CTA reduce (warp redux, then shared memory) and the cross-CTA step are lexicographic on
+//    (key, global vector index): the earliest vector that contains the global extreme wins.
+//    32-bit keys: one packed 64-bit word per direction, atomicMin / atomicMax + a ticket
+//    (packed_grid_reduce); 64-bit keys: one tagged 64-byte slot per CTA, polled by CTA 0
+//    (grid_reduce).
+//  * One warp of the finishing CTA finishes exactly: the winning min / max / first-NaN
 //    vectors (<= 32 elements each) are re-read with one element per lane and a ballot
 //    picks the first match; the unaligned head and the sub-vector tail of the array
 //    ride along as per-lane candidates.  That yields first-occurrence indices with the
@@ -60,8 +62,8 @@ struct ScanParams {
   uint32_t rem_owner;      // grid-stride tiles: the CTA that takes the partial tile
   uint32_t dyn_tiles;      // full tiles behind the static ones that CTAs claim at run time (0 = none)
   uint32_t dyn_koff;       // slot tile ids >= dyn_koff name claimed tiles (UINT32_MAX = none)
-  void* partials;          // gridDim.x x Best<Key>
-  uint32_t* ticket;        // zero-initialised, self-resetting (atomicInc wrap)
+  void* partials;          // gridDim.x x 64-byte tagged slots (grid_reduce, 64-bit keys)
+  uint32_t* ticket;        // scratch block, layout WS_* below
   amm_record* rec_dev;     // device record slot
   amm_record* rec_host;    // pinned + mapped host record slot (device address) or nullptr
   uint64_t seq;
@@ -433,7 +435,7 @@ __device__ __forceinline__ amm_record make_record(const ScanParams& p, const Bes
   return r;
 }
 
-// Last step of a call, executed by WARP 0 of the last CTA (all 32 lanes must call; `x` is read
+// Last step of a call, executed by WARP 0 of the finishing CTA (all 32 lanes must call; `x` is read
 // from lane 0).  world == 1: publish this GPU's record.  world > 1: the compute step is FUSED
 // with its collective -- instead of returning to the host for an NCCL all-gather, lane t stores
 // the 64-byte record straight into peer t's exchange buffer over NVLink (peer-mapped pointers),
@@ -561,7 +563,7 @@ __device__ __forceinline__ void finalize_warp(const ScanParams& p, const Best<Ke
 // follows a non-pipelined one, as in windows_huge).
 // Pipelined mode (amm_workspace_set_pipelined, caller promises that a scan's input is not
 // produced by the kernel right before it on the stream): the trigger is issued on entry and the
-// wait moves to the point where the CTA first touches the shared workspace (partials, ticket,
+// wait moves to the point where the CTA first touches the shared workspace (slots, ticket,
 // record slots), so the STREAMING phase of scan k+1 overlaps the fold / locate / publish tail
 // of scan k.
 __device__ __forceinline__ void pdl_launch_dependents() {
@@ -807,8 +809,8 @@ __device__ __forceinline__ bool packed_grid_reduce(const ScanParams& p, PackedCa
   return true;
 }
 
-// Shared-memory scratch of the cross-CTA step: Best<Key>[32] for the partials flow, 5 x 32 words
-// for the packed flow.
+// Shared-memory scratch of the CTA reduce: Best<Key>[32] (block_reduce), 5 x 32 words for the
+// packed flow.
 template <typename Key>
 struct alignas(16) ReduceScratch {
   static constexpr size_t BYTES = sizeof(Best<Key>) * 32 > 640 ? sizeof(Best<Key>) * 32 : 640;
@@ -1035,7 +1037,7 @@ __global__ void __launch_bounds__(DIRECT_MAX_THREADS) argminmax_direct_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------
-// Exact finish, executed by WARP 0 of the last CTA (all 32 lanes; the result is valid in lane 0):
+// Exact finish, executed by WARP 0 of the finishing CTA (all 32 lanes; the result is valid in lane 0):
 // the winning min / max / first-NaN vectors (`b` holds their VECTOR indices; <= 32 elements each)
 // are re-read with one element per lane and a ballot picks the first match; the unaligned head
 // and the sub-vector tail (< one vector each) ride along as exact per-lane candidates.  All five
@@ -1321,7 +1323,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
   }
 
   // ------------------- CTA + grid reduce on (key, global vector index); only warp 0 of the
-  // last CTA to arrive goes on, with the grid-wide candidates in `b`
+  // finishing CTA (last ticket / CTA 0) goes on, with the grid-wide candidates in `b`
   Best<Key> b;
   if constexpr (PACKED) {
     // 32-bit pieces (launch_one guarantees fewer than 2^32 - 2 vectors)
@@ -1342,7 +1344,7 @@ __global__ void __launch_bounds__(MAX_THREADS) argminmax_scan_kernel(const ScanP
     stamp(p, ST_CTA_REDUCED);
     if (!grid_reduce(p, b, scratch.best())) return;
   }
-  // every CTA has taken its ticket, hence made its last claim: re-arm the claim counter
+  // every CTA has passed the grid step, hence made its last claim: re-arm the claim counter
   if (dyn_tiles != 0 && threadIdx.x == 0) *dyn_counter = 0u;
   stamp(p, ST_GRID_FOLDED);
   const Best<Key> x = exact_finish_warp<P, VEC_ELEMS>(p, bd, b);

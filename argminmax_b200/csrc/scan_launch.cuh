@@ -200,7 +200,7 @@ static int launch_packed(amm_workspace* ws, ScanParams& p, int dtype_slot, int v
 }
 
 // 32-bit keys with fewer than 2^32 - 2 vectors: the cross-CTA step travels as packed 64-bit
-// words (see packed_grid_reduce); everything else keeps the partials + ticket + fold flow.
+// words (see packed_grid_reduce); everything else goes through the tagged slots (grid_reduce).
 template <class P, int VEC, int U, bool PF, int HINT, bool XCHG>
 static int launch_one(amm_workspace* ws, ScanParams& p, int dtype_slot, int variant,
                       cudaStream_t stream) {

@@ -94,8 +94,8 @@ typedef struct amm_workspace amm_workspace; /* per-device scratch + pinned resul
 typedef struct amm_sharded amm_sharded;     /* one workspace + stream per GPU + NCCL comms */
 
 /* ------------------------------------------------------------------ lifecycle */
-/* Scratch for calls on CUDA device `device` (block partials, ticket counter,
-   64-B device record, 64-B pinned+mapped host record).  No reference analogue:
+/* Scratch for calls on CUDA device `device` (per-CTA result slots, ticket and packed candidate
+   words, 64-B device record, 64-B pinned+mapped host record).  No reference analogue:
    the CPU path needs no scratch. */
 int amm_workspace_create(int device, amm_workspace** ws);
 int amm_workspace_destroy(amm_workspace* ws);
@@ -306,7 +306,7 @@ int amm_workspace_set_tuning(amm_workspace* ws, int threads, int ctas_per_sm, in
 int amm_workspace_set_pipelined(amm_workspace* ws, int on);
 /* Small inputs take the one-trip latency kernel (every thread holds its 1-4 vectors in registers:
    value-only fold, then the first matching element is located in registers; nothing is re-read)
-   instead of the streaming kernel: by default up to 2^20 elements for 1/2/4-byte dtypes and 2^16
+   instead of the streaming kernel: by default up to 2^20 elements for 1/2/4-byte dtypes and 2^19
    for 8-byte dtypes (the measured crossovers), and never more than four 16-byte vectors per
    thread.  This call replaces the size rule by "inputs of at most `bytes`"; 0 disables the
    latency kernel. */
@@ -342,7 +342,7 @@ int amm_debug_plan_scan(uint64_t base_addr, uint64_t n, int elem_size, int vec_b
                         uint64_t out[12]);
 /* Debug twin built with -DAMM_PHASE_STAMPS only (tools/phase_stamps.py): %globaltimer stamps of
    the most recent scan, 8 words per CTA (entry, first tile folded, streaming done, CTA reduced,
-   ticket taken; last CTA: grid folded, exact finish done, published).  The product library
+   grid step entered; finishing CTA: grid folded, exact finish done, published).  The product library
    returns AMM_ERR_ARG. */
 int amm_debug_read_stamps(amm_workspace* ws, uint64_t* out, int ctas);
 /* grid size and kernels launched by the most recent amm_argminmax_launch on ws */

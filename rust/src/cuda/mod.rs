@@ -96,7 +96,7 @@ impl CudaDType for half::f16 {
     const CODE: c_int = 8;
 }
 
-/// Per-device scratch (block partials, ticket, pinned result slot).  One per concurrent caller.
+/// Per-device scratch (per-CTA result slots, ticket and packed words, pinned result slot).  One per concurrent caller.
 pub struct Workspace {
     raw: *mut AmmWorkspace,
     device: i32,

@@ -333,3 +333,35 @@ def test_host_slice_pageable_bounce_ring():
                 ws.close()
             finally:
                 os.environ.pop("AMM_HOST_COPY_THREADS", None)
+
+
+@pytest.mark.parametrize("dt", G.ALL_DTYPES)
+def test_latency_kernel_regimes(dt):
+    """The one-trip latency kernel switches shape with the number of 16-byte vectors: one CTA of 256
+    or 512 threads (up to 2048 vectors and 16 Ki elements), then several CTAs with 1, 2, 3 or 4
+    vectors per thread (fused / select-based / lazy locate).  Every boundary, with a ragged tail and
+    an unaligned head, with duplicated extremes so that the first occurrence is what is checked."""
+    rng = np.random.default_rng(4242 + sum(map(ord, dt)))
+    ve = 16 // np.dtype(G.NP[dt]).itemsize
+    step = 148 * 2 * 256  # vectors per "vectors per thread" step on a 148-SM part
+    n_vecs = [255, 256, 257, 1023, 1024, 1025, 2047, 2048, 2049, 4096, step, step + 1, 2 * step, 2 * step + 1,
+              3 * step, 3 * step + 1, 4 * step - 7, 4 * step]
+    sizes = sorted({nv * ve + t for nv in n_vecs for t in (0, ve - 1)} | {16383, 16384, 16385})
+    for i, n in enumerate(sizes):
+        a = random_array(dt, n, rng)
+        if n > 64:
+            # duplicate the extremes at a few places behind their first occurrence
+            lo, hi = oracle.argminmax(a, 0)
+            for j in rng.integers(0, n, 6):
+                if j > lo and j != hi:
+                    a[j] = a[lo]
+            for j in rng.integers(0, n, 6):
+                if j > hi and j != lo and a[j] != a[lo]:
+                    a[j] = a[hi]
+        for mode in modes_for(dt):
+            b = a
+            if mode == 1 and i % 3 == 0 and n > 8:
+                b = a.copy()
+                b[[n // 2, n - 2]] = np.nan
+            assert_parity(b, mode, byte_offset=(i % 4) * np.dtype(G.NP[dt]).itemsize, what="latency regimes",
+                          paths=("default", "direct"))

@@ -19,7 +19,25 @@ import torch  # noqa: E402
 DT = {"i8": 0, "i16": 1, "i32": 2, "i64": 3, "u8": 4, "u16": 5, "u32": 6, "u64": 7, "f16": 8, "f32": 9, "f64": 10}
 
 
-def load(path):
+def load(path, env=""):
+    """Load `path` and create a workspace with the `K=V,K=V` environment overrides in force (the
+    library reads its knobs when a workspace is created)."""
+    saved = {}
+    for kv in [x for x in env.split(",") if x]:
+        k, v = kv.split("=", 1)
+        saved[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        return _load(path)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _load(path):
     lib = ctypes.CDLL(path)
     lib.amm_workspace_create.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
     lib.amm_workspace_destroy.argtypes = [ctypes.c_void_p]
@@ -42,17 +60,19 @@ def main():
     ap.add_argument("--max-log2", type=int, default=22)
     ap.add_argument("--calls", type=int, default=300)
     ap.add_argument("--rounds", type=int, default=7)
+    ap.add_argument("--env-a", default="", help="K=V,K=V knobs in force while A's workspace is created")
+    ap.add_argument("--env-b", default="")
     a = ap.parse_args()
     t = torch.randint(-2**31, 2**31 - 1, ((8 << a.max_log2) // 4 + 4,), dtype=torch.int32, device="cuda:0")
     torch.cuda.synchronize()
-    la, wa = load(a.a)
-    lb, wb = load(a.b)
+    la, wa = load(a.a, a.env_a)
+    lb, wb = load(a.b, a.env_b)
     out = (ctypes.c_double * 3)()
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     for dt in a.dtypes.split(","):
         if a.mode == 1 and dt not in ("f16", "f32", "f64"):
             continue
-        row = {"dtype": dt, "mode": a.mode, "a": os.path.basename(a.a), "b": os.path.basename(a.b), "us_a": {}, "us_b": {}, "b_minus_a": {}}
+        row = {"dtype": dt, "mode": a.mode, "a": os.path.basename(a.a) + " " + a.env_a, "b": os.path.basename(a.b) + " " + a.env_b, "us_a": {}, "us_b": {}, "b_minus_a": {}}
         for lg in range(a.min_log2, a.max_log2 + 1):
             n = 1 << lg
             ra, rb = [], []

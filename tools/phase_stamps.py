@@ -89,7 +89,7 @@ def main():
             assert rc == 0, rc
             st = np.frombuffer(out, dtype=np.uint64).reshape(grid, 8).astype(np.int64)
             t0 = st[:, 0].min()
-            last = int(np.argmax(st[:, 4]))  # the CTA that took the last ticket
+            last = int(np.argmax(st[:, 7]))  # the CTA that published (last ticket holder, or CTA 0 of the slot flow)
             rows.append({
                 "entry_spread": int(st[:, 0].max() - t0),
                 "first_fold_min": int(st[:, 1][st[:, 1] > 0].min() - t0) if (st[:, 1] > 0).any() else None,
