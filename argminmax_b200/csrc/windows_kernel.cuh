@@ -315,20 +315,58 @@ __device__ __forceinline__ Best<typename P::Key> window_to_keys(const Best<typen
   return k;
 }
 
+// One window folded by ALL threads of the CTA (THREADS x 4 x 16 bytes in flight, ~15-25 GB/s per
+// CTA): what the kernels below fall back to for a window far larger than the ones they were
+// launched for.  The kernel is chosen by the MEAN window size, and a lane group (1-32 lanes,
+// 0.03-3 GB/s from global memory) that runs into one window of, say, 100 MB among millions of
+// 500-byte ones would hold the whole launch up for seconds.  All threads must call.
+template <class P, int THREADS>
+__device__ __forceinline__ void window_by_cta(const WindowParams& p, uint64_t w, Best<typename WinCmp<P>::T>* smem /* [32] */) {
+  uint64_t begin, end;
+  window_bounds<P>(p, w, begin, end);
+  const WindowGeom<P, 16> g(p.base, begin, end);
+  Best<typename WinCmp<P>::T> x;
+  x.clear();
+  window_fold<P, THREADS, 4, 16>(p.base, g, threadIdx.x, x);
+  x = block_reduce(x, smem);
+  if (threadIdx.x < 32) window_locate_store<P, 32, 16>(p, w, true, g, window_to_keys<P>(x), threadIdx.x);
+}
+// a lane group of G lanes hands a window over to the whole CTA from this many bytes on
+template <int G>
+__device__ __forceinline__ bool window_is_oversized(uint64_t bytes) {
+  return bytes >= (uint64_t)G * 4096u + 32768u;
+}
+
 // one group of G lanes per window (32 / G windows per warp), grid-stride over windows
 template <class P, int G, int VECB = 16>
 __global__ void __launch_bounds__(256) argminmax_windows_warp_kernel(const WindowParams p) {
   using Key = typename P::Key;
   constexpr uint32_t PER_WARP = 32 / G;
+  constexpr uint32_t DEFER_CAP = 64;
+  __shared__ Best<typename WinCmp<P>::T> s_red[32];
+  __shared__ uint64_t s_big[DEFER_CAP];  // oversized windows met by this CTA: folded by all of it at the end
+  __shared__ uint32_t s_nbig;
+  if (threadIdx.x == 0) s_nbig = 0;
+  __syncthreads();
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
   const uint64_t n_rounds = (p.n_windows + PER_WARP - 1) / PER_WARP;
   for (uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n_rounds;
        r += warps) {
     const uint64_t w = r * PER_WARP + lane / G;
-    const bool active = w < p.n_windows;
+    bool active = w < p.n_windows;
     uint64_t begin = 0, end = 0;
     if (active) window_bounds<P>(p, w, begin, end);
+    // (the shuffle is executed by all 32 lanes: lane groups of one warp differ in `big`)
+    const bool big = active && window_is_oversized<G>((end - begin) * sizeof(typename P::Elem));
+    uint32_t slot = DEFER_CAP;
+    if (big && lane % G == 0) slot = atomicAdd(&s_nbig, 1u);
+    slot = __shfl_sync(0xFFFFFFFFu, slot, (int)(lane - lane % G));
+    if (big && slot < DEFER_CAP) {  // (a full list: the lane group folds it itself, as before)
+      if (lane % G == 0) s_big[slot] = w;
+      active = false;
+      begin = end = 0;
+    }
     const WindowGeom<P, VECB> g(p.base, begin, end);
     Best<typename WinCmp<P>::T> x;
     x.clear();
@@ -336,6 +374,9 @@ __global__ void __launch_bounds__(256) argminmax_windows_warp_kernel(const Windo
     window_group_reduce<P, G>(x);
     window_locate_store<P, G, VECB>(p, w, active, g, window_to_keys<P>(x), lane);
   }
+  __syncthreads();
+  const uint32_t nbig = s_nbig < DEFER_CAP ? s_nbig : DEFER_CAP;
+  for (uint32_t i = 0; i < nbig; ++i) window_by_cta<P, 256>(p, s_big[i], s_red);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -643,10 +684,16 @@ __global__ void __launch_bounds__(THREADS)
   extern __shared__ __align__(128) uint8_t dsm[];  // 2 stages x stage_bytes
   __shared__ __align__(8) uint64_t s_bar[2];
   __shared__ uint64_t s_range[2][2];  // staged byte range [a0, a1) of each stage
+  // general form: windows far beyond the stage (ragged offsets with outliers) are not folded by
+  // their 1-32 lanes from global memory but handed to the whole CTA (window_by_cta)
+  __shared__ Best<typename WinCmp<P>::T> s_red[FAST ? 1 : 32];
+  __shared__ uint64_t s_big[FAST ? 1 : THREADS];
+  __shared__ uint32_t s_nbig;
   const uint32_t tid = threadIdx.x, lane = tid & 31;
   const uint32_t wi = tid / L, l = tid % L;  // window in pass, lane in window
   const uint64_t n_blocks = (p.n_windows + WPBK - 1) / WPBK;
   const bool out16 = (((uint64_t)(uintptr_t)p.out) & 15) == 0;
+  if (tid == 0) s_nbig = 0;
 
   // thread 0: staged byte range of block `blk`, published in s_range[s], and the copy itself
   const uint32_t wvec = FAST ? (uint32_t)(p.window / WindowGeom<P>::VE) : 0;  // vectors per window
@@ -707,7 +754,7 @@ __global__ void __launch_bounds__(THREADS)
     for (uint32_t kp = 0; kp < kwin; ++kp) {
     const uint32_t wk = kp * WPB + wi;  // this lane group's window inside the block
     const uint64_t w = blk * WPBK + wk;
-    const bool active = w < p.n_windows;
+    bool active = w < p.n_windows;
     WinSrc src;
     src.base = p.base;
     src.stage_s = smem_u32(dsm) + s * stage_bytes;
@@ -721,9 +768,15 @@ __global__ void __launch_bounds__(THREADS)
       } else {
         uint64_t begin = 0, end = 0;
         if (active) window_bounds<P>(p, w, begin, end);
-        const WindowGeom<P> gg(p.base, begin, end);
         src.a0 = s_range[s][0];
         src.a1 = s_range[s][1];
+        if (active && window_is_oversized<L>((end - begin) * sizeof(Elem)) &&
+            !(begin * sizeof(Elem) >= src.a0 && end * sizeof(Elem) <= src.a1)) {
+          if (l == 0) s_big[atomicAdd(&s_nbig, 1u)] = w;  // at most WPB <= THREADS per block
+          active = false;
+          begin = end = 0;
+        }
+        const WindowGeom<P> gg(p.base, begin, end);
         const uint64_t vbyte = gg.a0 * sizeof(Elem);  // byte offset of unit 1
         src.vec_staged = vbyte >= src.a0 && vbyte + gg.nv * 16 <= src.a1;
         src.vec_s = src.stage_s + (uint32_t)(vbyte - src.a0);
@@ -816,6 +869,15 @@ __global__ void __launch_bounds__(THREADS)
     }
     }  // passes of the block
     __syncthreads();  // everyone is done with stage s: it may be refilled
+    if constexpr (!FAST) {
+      const uint32_t nbig = s_nbig;  // CTA-uniform
+      if (nbig != 0) {
+        for (uint32_t i = 0; i < nbig; ++i) window_by_cta<P, THREADS>(p, s_big[i], s_red);
+        __syncthreads();
+        if (tid == 0) s_nbig = 0;
+        __syncthreads();
+      }
+    }
   }
 }
 

@@ -307,3 +307,43 @@ def test_large_mean_but_all_windows_empty():
     offs = torch.tensor([0, 0, a.size, a.size], dtype=torch.int64, device="cuda:0")
     got = [tuple(r) for r in ds.argminmax_windows(offs, 0).cpu().tolist()]
     assert got == [(-1, -1), (0, a.size - 1), (-1, -1)]
+
+
+@pytest.mark.parametrize("dt", ["f32", "u8", "f64", "f16", "i64"])
+@pytest.mark.parametrize("mean", [40, 400, 1100])
+def test_ragged_windows_with_giant_outliers(dt, mean):
+    """The window kernel is chosen by the MEAN window size (1-8 lanes per window from a staged
+    block, 8 lanes or one warp per window from global memory).  Windows far beyond that -- here
+    0.3-1.5 M elements among tens of thousands of ~`mean`-element ones, at the front, in the
+    middle and at the end -- are handed to the whole CTA (window_by_cta) instead of keeping one
+    lane group busy for milliseconds; the answers do not change."""
+    import time
+
+    import torch
+    rng = np.random.default_rng(1000 + mean)
+    n = 6_000_000
+    a = random_array(dt, n, rng)
+    if dt in G.FLOAT_DTYPES:
+        a[rng.integers(0, n, 40)] = np.nan
+    ds, _keep = to_device(a)
+    giants = [1_500_000, 300_000, 700_000, 400_000]
+    n_small = (n - sum(giants)) // mean
+    small = rng.integers(max(1, mean // 2), mean + mean // 2 + 1, n_small)
+    k = n_small // 3
+    sizes = np.concatenate([[giants[0]], small[:k], [giants[1], 0, giants[2]], small[k:2 * k], small[2 * k:], [giants[3]]])
+    cuts = np.concatenate([[0], np.cumsum(sizes)])
+    cuts = cuts[cuts < n]
+    cuts = np.concatenate([cuts, [n]])
+    offs = torch.from_numpy(cuts.astype(np.int64)).cuda()
+    bounds = list(zip(cuts[:-1].tolist(), cuts[1:].tolist()))
+    for mode in modes_for(dt):
+        out = ds.argminmax_windows(offs, mode)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = ds.argminmax_windows(offs, mode)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        got = [tuple(r) for r in out.cpu().tolist()]
+        assert got == _expected(a, bounds, mode)
+        # a lane group walking 1.5 M elements alone took 10-200 ms; the CTA takes well under 2
+        assert ms < 5.0, (dt, mean, mode, ms)

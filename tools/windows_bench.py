@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--ragged", action="store_true",
                     help="ragged windows (offsets): lengths uniform in [W/2, 3W/2], the down-sampling-by-time case")
+    ap.add_argument("--outlier", type=int, default=0, help="with --ragged: one window of this many elements among them")
     a = ap.parse_args()
     g = torch.Generator(device="cuda:0").manual_seed(3)
     t = torch.empty(a.bytes // 4, dtype=torch.int32, device="cuda:0")
@@ -35,10 +36,16 @@ def main():
                 n = ds.n
                 nwin = max(1, n // w)
                 lens = torch.randint(max(1, w // 2), w + w // 2 + 1, (nwin,), device="cuda:0", dtype=torch.int64, generator=g)
+                # scale the running sum to end exactly at n: no giant / empty windows at the end
+                csum = torch.cumsum(lens, 0).to(torch.float64)
                 offs = torch.zeros(nwin + 1, dtype=torch.int64, device="cuda:0")
-                torch.cumsum(lens, 0, out=offs[1:])
-                offs = torch.clamp(offs, max=n)
+                offs[1:] = torch.floor(csum * (n / float(csum[-1]))).to(torch.int64)
                 offs[-1] = n
+                if a.outlier:
+                    # one window of `outlier` elements in the middle of the small ones
+                    mid = nwin // 2
+                    shift = min(a.outlier, n - int(offs[mid + 1]))
+                    offs[mid + 1:] = torch.clamp(offs[mid + 1:] + shift, max=n)
                 arg = offs
             for _ in range(2):
                 out = ds.argminmax_windows(arg)
@@ -49,7 +56,7 @@ def main():
             e1.record()
             e1.synchronize()
             ms = e0.elapsed_time(e1) / a.iters
-            print(json.dumps({"dtype": dt, "window": w, "ragged": bool(a.ragged), "n_windows": out.shape[0], "ms": round(ms, 4),
+            print(json.dumps({"dtype": dt, "window": w, "ragged": bool(a.ragged), "outlier": a.outlier, "n_windows": out.shape[0], "ms": round(ms, 4),
                               "GBps": round(a.bytes / ms / 1e6, 1)}), flush=True)
 
 
