@@ -633,7 +633,9 @@ def main() -> int:
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": committed_traffic(),
                 "traffic_source": "committed ncu --set full capture (profiles/traffic.json), not measured in this run",
-                "kernel": "argminmax_scan_kernel<PolF32<ignore>>", "kernel_ms": round(kernel_ms, 5),
+                "kernel": ("argminmax_ring_kernel<PolF32<ignore>>" if "ring" in str(tuning.get("variant_name", ""))
+                           else "argminmax_scan_kernel<PolF32<ignore>>"),
+                "kernel_ms": round(kernel_ms, 5),
                 "algorithmic_bytes_per_launch": nbytes, "peak_source": peak_src,
                 "note": "kernel_ms: serialised launches (each kernel alone on the GPU); `value` is measured with "
                         "consecutive steps pipelined (PDL), which hides each kernel's fold/publish tail",

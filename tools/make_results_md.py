@@ -2,6 +2,7 @@
 """Assemble RESULTS.md from the committed measurement files under profiles/ (round 2).
   python tools/make_results_md.py [--tag r02e] > RESULTS.md"""
 import argparse
+import collections
 import json
 import os
 
@@ -20,7 +21,7 @@ def one(name):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--tag", default="r02e")
+    ap.add_argument("--tag", default="r02g")
     ap.add_argument("--multi-tag", default="r02g")
     a = ap.parse_args()
     t = a.tag
@@ -132,19 +133,25 @@ def main():
         pass
 
     w(f"Small-n latency, synchronous C-ABI call from a C++ host program, f32, 1 GPU (`profiles/{t}_latency_c_f32.jsonl`; an EMPTY "
-      "kernel + result poll costs 6.5–7.2 µs on these boxes, `tools/exp/latency_floor.cu`):\n")
+      "kernel + result poll costs 6.5–7.5 µs on these boxes, `tools/exp/latency_floor.cu`; in brackets the state before the "
+      "last pass over the latency kernel, `r02e_latency_c_f32.jsonl`, another box):\n")
     w("| n | µs/call median | min | p99 |")
     w("|---:|---:|---:|---:|")
+    try:
+        before = {d["n"]: d["us_call_median"] for d in lines("r02e_latency_c_f32.jsonl")}
+    except OSError:
+        before = {}
     for d in lines(f"{t}_latency_c_f32.jsonl"):
-        w(f"| {d['n']:,} | {d['us_call_median']} | {d['us_call_min']} | {d['us_call_p99']} |")
+        o = f" ({before[d['n']]})" if d["n"] in before and t != "r02e" else ""
+        w(f"| {d['n']:,} | {d['us_call_median']}{o} | {d['us_call_min']} | {d['us_call_p99']} |")
     w(f"\nOther dtypes and return-NaN mode: `profiles/{t}_latency_all_dtypes.jsonl`. One array sharded over 8 GPUs, one host "
       "thread: 20–23 µs/call for 2^10…2^24 elements (launcher thread per device; one thread for all: 36–39 µs; NCCL: 120 µs) — "
       "`profiles/r02d_sharded_latency_8gpu_*.jsonl`.\n")
 
-    w(f"## Windowed / segmented form (SURVEY §8f-4) — 1 GiB of data, fixed windows, kernel-only (`profiles/{t}_windows_bench.jsonl`)\n")
+    w(f"## Windowed / segmented form (SURVEY §8f-4) — 1 GiB of data, fixed windows, kernel-only (`profiles/r02e_windows_bench.jsonl`)\n")
     w("GB/s of input (every window also writes 16 bytes of output); in brackets round 1 (`r01d_windows_bench_1gib.jsonl`) where it "
       "differs by more than 5 %.\n")
-    cur = {(d["dtype"], d["window"]): d["GBps"] for d in lines(f"{t}_windows_bench.jsonl")}
+    cur = {(d["dtype"], d["window"]): d["GBps"] for d in lines("r02e_windows_bench.jsonl")}
     try:
         old = {(d["dtype"], d["window"]): d["GBps"] for d in lines("r01d_windows_bench_1gib.jsonl")}
     except OSError:
@@ -170,6 +177,66 @@ def main():
       "`tests/test_gpu_reference_scale.py` (per window == oracle on the sub-slice; 10 000 × 129 and 500 × 5000 arrays per "
       "dtype and mode in one launch each).\n")
 
+    # ---- short windows before the value-domain compares (previous state, other box)
+    try:
+        sh = collections.defaultdict(dict)
+        for d in lines("r02f_windows_bench_short.jsonl"):
+            sh[d["window"]][d["dtype"]] = d["GBps"]
+        w("## Short windows before the value-domain compares (`profiles/r02f_windows_bench_short.jsonl`, another box)\n")
+        w("Several passes per block for 16-64-byte windows, packed-equality locate for 8-bit ints and f16, vector pairs for "
+          "8-byte dtypes; GB/s of input. (The table above is the final state: f32 / f64 additionally compare values instead "
+          "of ord keys.)\n")
+        w("| elements per window | " + " | ".join(dts) + " |")
+        w("|---:|" + "---:|" * len(dts))
+        for win in sorted(sh):
+            w(f"| {win:,} | " + " | ".join(f"{sh[win][dt]:.0f}" if dt in sh[win] else "–" for dt in dts) + " |")
+        w("")
+    except OSError:
+        pass
+
+    # ---- ragged windows (offsets), and what one oversized window costs
+    try:
+        rg = collections.defaultdict(dict)
+        for d in lines("r02g_windows_ragged.jsonl"):
+            rg[d["window"]][d["dtype"]] = d["GBps"]
+        rdt = ["f32", "u8", "f16", "f64"]
+        w("## Ragged windows (`amm_argminmax_windows`, offsets) — 1 GiB of data, lengths uniform in [W/2, 3W/2] "
+          "(`profiles/r02g_windows_ragged.jsonl`, `tools/windows_bench.py --ragged`)\n")
+        w("GB/s of input. Ragged windows always take the general staged form (64-bit window bounds, staged-range tests, "
+          "clamps): 1.2-4 x below fixed windows of the same mean size up to ~1 KB per window, level from 4 Ki elements on. "
+          "Known gap (DESIGN.md, section 10).\n")
+        w("| mean elements per window | " + " | ".join(rdt) + " |")
+        w("|---:|" + "---:|" * len(rdt))
+        for win in sorted(rg):
+            w(f"| {win:,} | " + " | ".join(f"{rg[win][dt]:.0f}" if dt in rg[win] else "–" for dt in rdt) + " |")
+        ob = {(d["dtype"], d["window"]): d["ms"] for d in lines("r02g_windows_ragged_outlier_before.jsonl")}
+        oa = {(d["dtype"], d["window"]): d["ms"] for d in lines("r02g_windows_ragged_outlier.jsonl")}
+        w("\nOne window of 25 M elements among them (the kernel is chosen by the MEAN window size; a lane group of 1-32 "
+          "lanes used to fold the outlier alone, now the whole CTA does, `window_by_cta`), ms per call, before -> after "
+          "(`r02g_windows_ragged_outlier{_before,}.jsonl`): "
+          + "; ".join(f"{dt} x {win}: {ob[(dt, win)]:.1f} -> {oa[(dt, win)]:.1f}" for (dt, win) in sorted(ob) if (dt, win) in oa)
+          + ". Parity: `tests/test_gpu_windows.py::test_ragged_windows_with_giant_outliers`.\n")
+    except OSError:
+        pass
+
+    # ---- last pass over the latency kernel: in-process A/B
+    try:
+        ab = [d for d in lines("r02g_latency_ab_inproc.jsonl")]
+        w("## Call latency before / after the last pass over the latency kernel — in-process A/B "
+          "(`profiles/r02g_latency_ab_inproc.jsonl`, `tools/exp/latency_ab.py`)\n")
+        w("Both builds loaded side by side and timed in alternation (7 rounds x 300 calls per size), µs per synchronous call, "
+          "previous commit -> working tree: fused / select-based / lazy locate, one CTA up to 32 KiB, redux-based CTA reduce, "
+          "tagged-slot grid step for 64-bit keys.\n")
+        sizes = ["10", "12", "13", "14", "16", "18", "20", "22"]
+        w("| dtype, mode | " + " | ".join(f"2^{k}" for k in sizes) + " |")
+        w("|---|" + "---:|" * len(sizes))
+        for d in ab:
+            w(f"| {d['dtype']}, {'return-NaN' if d['mode'] else 'ignore-NaN'} | "
+              + " | ".join(f"{d['us_a'][k]:.2f} → {d['us_b'][k]:.2f}" for k in sizes) + " |")
+        w("")
+    except OSError:
+        pass
+
     cb = b1.get("cpu_baseline") or {}
     ref = one(f"{t}_bench_reference_arm.json")
     w(f"## CPU baseline on the GPU box's host ({cb.get('cpu_model', 'Intel Xeon')}, {cb.get('host_cpus', 16)} vCPUs, AVX-512)\n")
@@ -178,7 +245,7 @@ def main():
       f"(same `config` dict as our arm, 2^30 elements per step): {ref['value']} GB/s, {ref['ms_per_step']} ms per step. "
       f"{cb.get('all_cores_not_reference', {}).get('threads')} threads, contiguous shards + ordered combine (NOT something the reference does): "
       f"{cb.get('all_cores_not_reference', {}).get('value')} GB/s.")
-    hp = lines(f"{t}_host_pageable.jsonl")
+    hp = lines("r02e_host_pageable.jsonl")
     w("\nHost slices in pageable vs pinned memory (`amm_host_argminmax`, 1 GiB f32): "
       + "; ".join(f"{d['memory']}: {d['GBps_best']} GB/s" for d in hp) + ".")
     print("\n".join(out))
