@@ -33,4 +33,19 @@ AMM_HD uint64_t mix_checksum(const uint64_t* w /* [8] */, uint64_t seed) {
 constexpr uint64_t HOST_SLOT_SEED = 0xA5A5C3C3F00DBEEFull;
 constexpr uint64_t PEER_SLOT_SEED = 0x5EEDFACE0DDBA11ull;
 
+// Integrity word of a per-CTA grid slot (scan_kernel.cuh: grid_reduce): five data words, seeded
+// with the call's sequence number and the slot index, so a slot that still holds an older call's
+// record -- or another slot's -- does not pass.  Never 0: a zeroed slot (fresh workspace) cannot
+// pass whatever the seed.
+constexpr uint64_t GRID_SLOT_SEED = 0xC0FFEE0DD5107ull;
+AMM_HD uint64_t grid_slot_check(const uint64_t (&w)[5], uint64_t seq, uint32_t slot) {
+  uint64_t c = GRID_SLOT_SEED ^ seq ^ ((uint64_t)slot << 48);
+  for (int i = 0; i < 5; ++i) {
+    c = (c ^ w[i]) * 0x9E3779B97F4A7C15ull;
+    c = (c << 23) | (c >> 41);
+    c += (uint64_t)(i + 1);
+  }
+  return c | 1ull;
+}
+
 }  // namespace amm

@@ -594,18 +594,6 @@ __device__ __forceinline__ void pdl_entry(const ScanParams& p) {
 // grids larger than the GPU are fine.
 // Returns true in warp 0 of CTA 0 only (all 32 lanes), with `b` = the grid-wide result.  `b` must
 // be the CTA-wide result in every thread (block_reduce) on entry.
-constexpr uint64_t GRID_SLOT_SEED = 0xC0FFEE0DD5107ull;
-__device__ __forceinline__ uint64_t grid_slot_check(const uint64_t (&w)[5], uint64_t seq, uint32_t slot) {
-  uint64_t c = GRID_SLOT_SEED ^ seq ^ ((uint64_t)slot << 48);
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    c = (c ^ w[i]) * 0x9E3779B97F4A7C15ull;
-    c = (c << 23) | (c >> 41);
-    c += (uint64_t)(i + 1);
-  }
-  return c | 1ull;  // never 0: a zeroed slot (fresh workspace) cannot pass
-}
-
 template <typename Key>
 __device__ __forceinline__ bool grid_reduce(const ScanParams& p, Best<Key>& b, Best<Key>* smem) {
   pdl_wait_prior_grid();  // from here on the workspace is ours

@@ -55,6 +55,28 @@ int main() {
     }
   // the seed (the call's tag for peer slots) is part of it
   CHECK(mix_checksum(r, amm::PEER_SLOT_SEED ^ 1) != mix_checksum(r, amm::PEER_SLOT_SEED ^ 2));
+  // ---- per-CTA grid slots (grid_reduce): five words + integrity word seeded with (seq, slot)
+  {
+    using amm::grid_slot_check;
+    const uint64_t zero[5] = {0, 0, 0, 0, 0};
+    uint64_t d[5] = {(uint64_t)-5, 9, 1234, 77, ~0ull};
+    for (uint64_t seq = 1; seq < 2000; ++seq)
+      for (uint32_t slot = 0; slot < 600; slot += 37) {
+        CHECK(grid_slot_check(zero, seq, slot) != 0);            // a zeroed slot never passes
+        CHECK(grid_slot_check(d, seq, slot) != grid_slot_check(d, seq + 1, slot));   // older call
+        CHECK(grid_slot_check(d, seq, slot) != grid_slot_check(d, seq, slot + 1));   // other slot
+      }
+    // torn between two calls' records of the same slot (16-byte pieces: words 01 | 23 | 4c)
+    uint64_t o[5] = {3, 9, 10, 20, ~0ull}, n[5] = {9, 3, 20, 10, ~0ull};
+    const uint64_t cn = grid_slot_check(n, 8, 5);
+    for (int mask = 1; mask < 3; ++mask) {
+      uint64_t m[5];
+      for (int i = 0; i < 5; ++i) m[i] = ((mask >> (i / 2)) & 1) ? o[i] : n[i];
+      CHECK(grid_slot_check(m, 8, 5) != cn);
+    }
+    // the new data with the OLD call's integrity word
+    CHECK(grid_slot_check(n, 7, 5) != cn);
+  }
   if (failures == 0) printf("record_slot_check ok\n");
   return failures != 0;
 }
