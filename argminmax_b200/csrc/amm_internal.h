@@ -43,7 +43,7 @@ struct amm_workspace {
   int direct_one_cta_vecs;  // inputs of up to this many 16-byte vectors (and 16 Ki elements) take ONE CTA
   int scan_packed;        // the same cross-CTA step in the streaming kernel (AMM_SCAN_PACKED=0: off)
   int scan_dyn_pct;       // share of the tiles claimed at run time: -1 automatic, 0 none, 1..90 percent (AMM_SCAN_DYN_PCT)
-  int scan_ring;          // TMA-ring kernel: -1 automatic (inputs >= 512 MiB), 0 never, 1 always (AMM_SCAN_RING)
+  int scan_ring;          // TMA-ring kernel: -1 automatic (inputs >= 2 GiB), 0 never, 1 always (AMM_SCAN_RING)
   int ring_ctas_per_sm;   // ... CTAs per SM (2: 2 x 96 KiB of stages; AMM_RING_CTAS)
   int ring_ready[AMM_POLICY_SLOTS][4];  // ... dynamic shared memory opted in (per instantiation)
   int scan_dyn_pipelined; // claimed tail also for pipelined scans (AMM_SCAN_DYN_PIPELINED=0: off)
