@@ -71,6 +71,7 @@ SIGNATURES = {
     "amm_device_uuid": (_i, [_i, _vp]),
     "amm_debug_read_stamps": (_i, [_vp, _u64p, _i]),
     "amm_debug_plan_scan": (_i, [_u64, _u64, _i, _i, _i, _i, _u64, _i, _i, _i, _i, _u64p]),
+    "amm_debug_plan_direct": (_i, [_u64, _u64, _i, _i, _i, _i, _i, _i, _u64p]),
     "amm_exchange_connect_ptrs": (_i, [_vp, ctypes.POINTER(_vp)]),
     "amm_exchange_local_buffer": (_i, [_vp, ctypes.POINTER(_vp)]),
     "amm_argminmax_launch_exchange": (_i, [_i, _vp, _u64, _i, _u64, _vp, _vp]),

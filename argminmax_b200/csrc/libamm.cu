@@ -1016,6 +1016,22 @@ int amm_debug_plan_scan(uint64_t base_addr, uint64_t n, int elem_size, int vec_b
   return AMM_OK;
 }
 
+/* Pure host logic of the latency kernel's launch shape (scan_launch.cuh: plan_direct), exposed for
+   the CPU test-suite.  out[0..6] = head_elems, n_vec, tail_start, grid, threads, vectors per thread,
+   fits (0: the input does not fit one trip -> streaming kernel). */
+int amm_debug_plan_direct(uint64_t base_addr, uint64_t n, int elem_size, int sm_count, int ctas_per_sm,
+                          int threads, int min_vpt, int one_cta_vecs, uint64_t out[8]) {
+  if (!out || n == 0 || sm_count < 1 || ctas_per_sm < 1 || threads < 32 || threads % 32 || threads > MAX_THREADS ||
+      min_vpt < 1 || (elem_size != 1 && elem_size != 2 && elem_size != 4 && elem_size != 8) ||
+      base_addr % (uint64_t)elem_size)
+    return AMM_ERR_ARG;
+  const DirectPlanKnobs knobs = {sm_count, ctas_per_sm, threads, min_vpt, one_cta_vecs};
+  const DirectPlan pl = plan_direct(base_addr, n, (uint32_t)elem_size, knobs);
+  const uint64_t v[8] = {pl.head_elems, pl.n_vec, pl.tail_start, pl.grid, pl.threads, pl.vpt, pl.fits ? 1u : 0u, 0};
+  memcpy(out, v, sizeof(v));
+  return AMM_OK;
+}
+
 /* AMM_PHASE_STAMPS builds only (tools/phase_stamps.py): copies the %globaltimer stamps of the
    most recent scan, 8 words per CTA, for `ctas` CTAs.  Other builds: AMM_ERR_ARG. */
 int amm_debug_read_stamps(amm_workspace* ws, uint64_t* out, int ctas) {

@@ -266,46 +266,69 @@ static int launch_ring(amm_workspace* ws, ScanParams& p, int dtype_slot, cudaStr
   return launch_ring_packed<P, XCHG, false>(ws, p, dtype_slot, stream);
 }
 
-// Latency path for small inputs: one trip, see argminmax_direct_kernel.  Returns false when the
-// input does not fit one trip (more than 4 vectors per thread at the CTA cap).
+// Latency path for small inputs: one trip, see argminmax_direct_kernel.
+// Shape of the launch, pure host logic (tests/test_direct_plan.py replays it through
+// amm_debug_plan_direct).  Latency, not throughput: as long as CTAs are available every thread
+// gets ONE vector (more CTAs are free latency); beyond sm_count x ctas_per_sm CTAs threads take
+// 2..4 vectors, all in flight at once.  Small inputs take ONE CTA -- `threads` (256) threads up to
+// 4 x threads vectors, 512 threads up to one_cta_vecs (2048 vectors = 32 KiB) and 16 Ki elements:
+// a second CTA brings in the cross-CTA round trip (~1 us; in-process A/B,
+// profiles/r02g_latency_ab_inproc.jsonl: 8 Ki f32 9.65 -> 8.6 us, 16 Ki f16 9.85 -> 8.9, 4 Ki i64
+// 10.5 -> 8.4).  Few deep threads beat many shallow ones (4 Ki f32: 8.6 us as 256 x 4, 9.4 as
+// 1024 x 1), but one SM folding 64 KiB is no faster than 16 SMs plus the round trip (u8 x 64 Ki in
+// one CTA: 11.1 us against 9.3).
+struct DirectPlanKnobs {
+  int sm_count, ctas_per_sm, threads, min_vpt, one_cta_vecs;
+};
+struct DirectPlan {
+  uint64_t head_elems, n_vec, tail_start, grid;
+  uint32_t threads, vpt;
+  bool fits;  // false: more than 4 vectors per thread at the CTA cap -> streaming kernel
+};
+static DirectPlan plan_direct(uint64_t addr, uint64_t n, uint32_t es, const DirectPlanKnobs& k) {
+  constexpr uint64_t VEC = 16;
+  DirectPlan pl;
+  const uint64_t vec_elems = VEC / es;
+  uint64_t head = ((VEC - (addr % VEC)) % VEC) / es;
+  if (head > n) head = n;
+  pl.head_elems = head;
+  pl.n_vec = (n - head) / vec_elems;
+  pl.tail_start = head + pl.n_vec * vec_elems;
+  uint64_t threads = (uint64_t)k.threads;
+  const uint64_t cap = (uint64_t)k.sm_count * (uint64_t)k.ctas_per_sm;
+  pl.fits = n / vec_elems <= cap * threads * 4;
+  uint64_t vpt = (pl.n_vec + cap * threads - 1) / (cap * threads);
+  if (vpt < (uint64_t)k.min_vpt) vpt = (uint64_t)k.min_vpt;
+  if (pl.n_vec > threads * 4 && pl.n_vec <= (uint64_t)k.one_cta_vecs &&
+      pl.n_vec <= (uint64_t)DIRECT_MAX_THREADS * 4 && n <= 16384)
+    threads = DIRECT_MAX_THREADS;
+  if (pl.n_vec <= threads * 4) vpt = (pl.n_vec + threads - 1) / threads;
+  if (vpt < 1) vpt = 1;
+  if (vpt > 4) pl.fits = false;
+  pl.threads = (uint32_t)threads;
+  pl.vpt = (uint32_t)vpt;
+  pl.grid = (pl.n_vec + threads * vpt - 1) / (threads * vpt);
+  if (pl.grid < 1) pl.grid = 1;
+  return pl;
+}
+static DirectPlanKnobs direct_knobs(const amm_workspace* ws) {
+  return {ws->sm_count, ws->direct_ctas_per_sm, ws->direct_threads, ws->direct_vecs_per_thread, ws->direct_one_cta_vecs};
+}
+
 template <class P>
 static bool direct_fits(const amm_workspace* ws, uint64_t n) {
-  const uint64_t vec_elems = 16 / sizeof(typename P::Elem);
-  const uint64_t cap_threads = (uint64_t)ws->sm_count * (uint64_t)ws->direct_ctas_per_sm * (uint64_t)ws->direct_threads;
-  return n / vec_elems <= cap_threads * 4;
+  return plan_direct(0, n, (uint32_t)sizeof(typename P::Elem), direct_knobs(ws)).fits;
 }
 
 template <class P>
 static int launch_direct(amm_workspace* ws, ScanParams& p, cudaStream_t stream) {
-  constexpr uint64_t VEC = 16;
-  const uint64_t vec_elems = VEC / sizeof(typename P::Elem);
-  const uint64_t addr = (uint64_t)(uintptr_t)p.base;
-  uint64_t head = ((VEC - (addr % VEC)) % VEC) / sizeof(typename P::Elem);
-  if (head > p.n) head = p.n;
-  p.head_elems = head;
-  p.n_vec = (p.n - head) / vec_elems;
-  p.tail_start = head + p.n_vec * vec_elems;
-  uint64_t threads = (uint64_t)ws->direct_threads;
-  // Latency, not throughput: as long as CTAs are available every thread gets ONE vector (more
-  // CTAs are free latency); beyond sm_count x direct_ctas_per_sm CTAs threads take 2..4 vectors,
-  // all in flight at once.  Small inputs take ONE CTA -- 256 threads up to 1024 vectors, 512
-  // threads up to direct_one_cta_vecs (2048 vectors = 32 KiB) and 16 Ki elements: a second CTA
-  // brings in the cross-CTA round trip (~1 us; in-process A/B, profiles/r02g_latency_ab.jsonl:
-  // 8 Ki f32 9.65 -> 8.6 us, 16 Ki f16 9.85 -> 8.9, 4 Ki i64 10.5 -> 9.2).  Few deep threads beat
-  // many shallow ones (4 Ki f32: 8.6 us as 256 x 4, 9.4 as 1024 x 1), but one SM folding 64 KiB is
-  // no faster than 16 SMs plus the round trip (u8 x 64 Ki in one CTA: 11.1 us against 9.3).
-  const uint64_t cap = (uint64_t)ws->sm_count * (uint64_t)ws->direct_ctas_per_sm;
-  uint64_t vpt = (p.n_vec + cap * threads - 1) / (cap * threads);
-  if (vpt < (uint64_t)ws->direct_vecs_per_thread) vpt = (uint64_t)ws->direct_vecs_per_thread;
-  if (p.n_vec > threads * 4 && p.n_vec <= (uint64_t)ws->direct_one_cta_vecs &&
-      p.n_vec <= (uint64_t)DIRECT_MAX_THREADS * 4 && p.n <= 16384)
-    threads = DIRECT_MAX_THREADS;
-  if (p.n_vec <= threads * 4) vpt = (p.n_vec + threads - 1) / threads;
-  if (vpt < 1) vpt = 1;
-  if (vpt > 4) return AMM_ERR_ARG;  // launch_variant checks direct_fits() first
-  p.direct_vpt = (uint32_t)vpt;
-  uint64_t grid = (p.n_vec + threads * vpt - 1) / (threads * vpt);
-  if (grid < 1) grid = 1;
+  const DirectPlan pl = plan_direct((uint64_t)(uintptr_t)p.base, p.n, (uint32_t)sizeof(typename P::Elem), direct_knobs(ws));
+  if (!pl.fits) return AMM_ERR_ARG;  // launch_variant checks direct_fits() first
+  p.head_elems = pl.head_elems;
+  p.n_vec = pl.n_vec;
+  p.tail_start = pl.tail_start;
+  p.direct_vpt = pl.vpt;
+  const uint64_t grid = pl.grid, threads = pl.threads;
   const bool packed = sizeof(typename P::Key) == 4 && p.n < 0xFFFFFFFEull && ws->direct_packed;
   if (p.world > 1) {
     if constexpr (sizeof(typename P::Key) == 4) {

@@ -340,6 +340,10 @@ int amm_debug_plan_window_chunks(const uint64_t* begins, const uint64_t* ends, u
 int amm_debug_plan_scan(uint64_t base_addr, uint64_t n, int elem_size, int vec_bytes, int u, int threads,
                         uint64_t grid_cap, int sm_count, int pipelined, int scan_contig, int scan_dyn_pct,
                         uint64_t out[12]);
+/* The same for the one-trip latency kernel (scan_launch.cuh: plan_direct; tests/test_direct_plan.py):
+   out[0..6] = head_elems, n_vec, tail_start, grid, threads, vectors per thread, fits. */
+int amm_debug_plan_direct(uint64_t base_addr, uint64_t n, int elem_size, int sm_count, int ctas_per_sm,
+                          int threads, int min_vpt, int one_cta_vecs, uint64_t out[8]);
 /* Debug twin built with -DAMM_PHASE_STAMPS only (tools/phase_stamps.py): %globaltimer stamps of
    the most recent scan, 8 words per CTA (entry, first tile folded, streaming done, CTA reduced,
    grid step entered; finishing CTA: grid folded, exact finish done, published).  The product library
