@@ -345,5 +345,6 @@ def test_ragged_windows_with_giant_outliers(dt, mean):
         ms = (time.perf_counter() - t0) * 1e3
         got = [tuple(r) for r in out.cpu().tolist()]
         assert got == _expected(a, bounds, mode)
-        # a lane group walking 1.5 M elements alone took 15-200 ms; the CTA takes 1-3
-        assert ms < 8.0, (dt, mean, mode, ms)
+        # a lane group walking 1.5 M 8-byte elements alone took 15-200 ms; the CTA takes 1-3 (wide margin:
+        # this is a guard against the pathology coming back, not a benchmark)
+        assert ms < 30.0, (dt, mean, mode, ms)
